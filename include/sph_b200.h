@@ -1,0 +1,117 @@
+/* sph_b200.h -- C ABI of the B200-native SPH solver step (libsph_b200.so).
+ *
+ * This is the drop-in boundary.  It replaces the reference's host->device interface
+ *   source/CUDA/System.cuh:1-37   (threadSync, allocateArray, copyTo/FromDevice, setParameters,
+ *                                  integrate, calcHash, reorder, collide)
+ *   source/CUDA/radixsort.cuh:30-32 (RadixSort)
+ * which `class cSPH` (source/SPH/SPH.h:9-50) drives from cSPH::Update (source/SPH/SPH_Update.cpp:12-81).
+ * The reference interface is void-returning, exits the process on a CUDA error and passes positions
+ * as OpenGL buffer ids; this one uses an opaque handle, int status codes, plain pointers and sizes,
+ * and owns its device buffers.  The cSPH-shaped C++ class in sph_host.h sits on top of it, and
+ * INTEGRATION.md shows the binding the reference's SPH layer would add.
+ *
+ * Threading: one handle = one device + one CUDA stream; calls on a handle must come from one thread
+ * at a time (the reference is driven from the single GLUT thread).  Calls are asynchronous on the
+ * handle's stream unless stated otherwise; every function that hands data to the host synchronises.
+ *
+ * There is no CPU fallback: every entry point fails with SPH_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "sph_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sph_system sph_t;
+
+enum sph_status {
+    SPH_OK = 0,
+    SPH_ERR_ARG = 1,        /* bad argument (null handle, range outside [0,numParticles), ...)   */
+    SPH_ERR_CUDA = 2,       /* a CUDA call failed; sph_last_error() has the text                 */
+    SPH_ERR_PARAMS = 3,     /* SimParams rejected (grid < 4 cells in a dimension, numCells mismatch) */
+    SPH_ERR_STATE = 4       /* call not valid in the current state                               */
+};
+
+/* which particle array */
+enum sph_array {
+    SPH_POS = 0,            /* float4 xyzw, ORIGINAL particle order (cSPH::getArray(false))      */
+    SPH_VEL = 1,            /* float4 xyzw, ORIGINAL particle order (cSPH::getArray(true))       */
+    SPH_DENSITY = 2,        /* float, original order                                             */
+    SPH_PRESSURE = 3,       /* float, original order                                             */
+    SPH_COLOR = 4,          /* float4, original order (the reference's colorVbo contents)        */
+    SPH_DYE = 5             /* float, original order (dDyeColor)                                 */
+};
+
+/* scratch of the last step, for parity tests (sph_debug_dump) */
+enum sph_dump {
+    SPH_DUMP_SORTED_PAIRS = 0,  /* uint32[2n]: (cellHash, originalIndex) in sorted order == reference dParHash[0] after RadixSort */
+    SPH_DUMP_CELL_START   = 1,  /* uint32[numCells]: first sorted index of each cell, 0xffffffff if empty == reference dCellStart */
+    SPH_DUMP_SORTED_POS   = 2,  /* float4[n]  == dSortedPos */
+    SPH_DUMP_SORTED_VEL   = 3,  /* float4[n]  == dSortedVel */
+    SPH_DUMP_PRESSURE     = 4,  /* float[n], sorted order == dPressure */
+    SPH_DUMP_DENSITY      = 5,  /* float[n], sorted order == dDensity  */
+    SPH_DUMP_NEIGHBOR_COUNTS = 6, /* uint32[n], sorted order: visited j!=i with r2<h2 in the density walk */
+    SPH_DUMP_CELL_END     = 7   /* uint32[numCells]: one past the last sorted index of each cell (start==end if empty) */
+};
+
+/* per-stage device time of the last sph_step call, milliseconds (sph_get_timings) */
+enum sph_stage {
+    SPH_STAGE_INTEGRATE_HASH = 0,   /* boundary + integrate + cell hash + cell histogram  (integrate, calcHash) */
+    SPH_STAGE_SORT = 1,             /* cell-table scan + deterministic stable counting sort (RadixSort)         */
+    SPH_STAGE_REORDER = 2,          /* gather into sorted SoA float4 buffers               (reorder)            */
+    SPH_STAGE_DENSITY = 3,          /* computeDensityD                                     (collide, 1st half)  */
+    SPH_STAGE_FORCE = 4,            /* computeForceD                                       (collide, 2nd half)  */
+    SPH_STAGE_COUNT = 5
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Allocates every buffer for params->numParticles / params->numCells on `device` (replaces
+ * cSPH::_InitMem + setParameters, SPH_Mem.cpp:11-54).  Positions/velocities start as zeros. */
+int sph_create(const struct SimParams* params, int device, sph_t** out);
+int sph_destroy(sph_t* s);                                   /* cSPH::_FreeMem, SPH_Mem.cpp:59-82 */
+
+/* ---- parameters ---------------------------------------------------------------------------- */
+/* Replaces setParameters (System.cu:634-637).  Takes effect at the next step.  numParticles,
+ * numCells and gridSize must not exceed what sph_create allocated. */
+int sph_set_params(sph_t* s, const struct SimParams* params);
+int sph_get_params(sph_t* s, struct SimParams* out);
+
+/* ---- stepping ------------------------------------------------------------------------------ */
+/* nsteps x { integrate -> hash -> sort -> reorder -> density -> force }, the stage order of
+ * cSPH::Update (SPH_Update.cpp:39-80).  Asynchronous. */
+int sph_step(sph_t* s, int nsteps);
+int sph_sync(sph_t* s);                                      /* threadSync, System.cu:613 */
+
+/* ---- particle arrays, original particle order ---------------------------------------------- */
+/* cSPH::setArray (SPH_Util.cpp:59-71): overwrite particles [start, start+count) from host memory. */
+int sph_set_array(sph_t* s, int which /*SPH_POS|SPH_VEL*/, const float* xyzw, int start, int count);
+/* cSPH::getArray (SPH_Util.cpp:44-56) generalised to a range and to the scalar arrays.  Blocking. */
+int sph_get_array(sph_t* s, int which, float* out, int start, int count);
+/* Device-resident variants (no host copy): src/dst are device pointers on the handle's device. */
+int sph_set_array_device(sph_t* s, int which, const float* d_xyzw, int start, int count);
+int sph_get_array_device(sph_t* s, int which, float* d_out, int start, int count);
+
+/* Replaces getPosBuffer() (SPH.h:29): device pointers of the live buffers in SORTED order plus the
+ * original-index array, for a renderer or a halo exchange that does not care about particle order.
+ * Valid until the next sph_step / sph_set_array. */
+int sph_device_buffers(sph_t* s, const float** d_pos, const float** d_vel, const uint32_t** d_index,
+                       const uint32_t** d_cellStart /* numCells+1 entries */);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int sph_debug_dump(sph_t* s, int what, void* out, size_t outBytes);      /* blocking */
+int sph_get_timings(sph_t* s, float* msPerStage /*[SPH_STAGE_COUNT]*/, int enable);
+/* device time of each of the last stepped stage kernels is only recorded when enabled */
+int sph_kernel_launch_count(sph_t* s, long long* launches);             /* kernels launched so far */
+void* sph_cuda_stream(sph_t* s);                                         /* cudaStream_t of the handle */
+const char* sph_last_error(sph_t* s);                                    /* s may be NULL: last create error */
+const char* sph_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

@@ -1,0 +1,362 @@
+// sph_capi.cu -- the C ABI of include/sph_b200.h: buffer ownership, stage sequencing, accessors.
+//
+// Takes the place of the reference's host wrappers (source/CUDA/System.cu:613-756) and of the
+// sequencing in cSPH::Update (source/SPH/SPH_Update.cpp:12-81): one stream, no host
+// synchronisation inside a step, no texture binds, no GL map/unmap.
+#include "sph_b200.h"
+#include "sph_device.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+struct sph_system {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    SimParams par;
+    int nAlloc = 0, cellsAlloc = 0;
+
+    float4 *pos[2] = {nullptr, nullptr}, *vel = nullptr, *velS = nullptr, *posP = nullptr, *velD = nullptr, *io = nullptr;
+    uint32_t *idx[2] = {nullptr, nullptr}, *keyU = nullptr, *rankU = nullptr, *keyS = nullptr, *counts = nullptr;
+    uint2* pairT = nullptr;
+    uint32_t *cellCount = nullptr, *cellStart = nullptr, *tileSums = nullptr, *maxCount = nullptr;
+    int cur = 0;                    // live pos/idx buffer
+    bool stepped = false;           // sorted scratch (keyS, posP, velD, cellStart) is valid
+    bool wantCounts = false;
+
+    SphPairConfig cfgDensity, cfgForce;
+    long long launches = 0;
+
+    bool timing = false;
+    cudaEvent_t ev[SPH_STAGE_COUNT + 1] = {};
+    float stageMs[SPH_STAGE_COUNT] = {};
+
+    std::string err;
+};
+
+static std::string g_createError;
+
+static int fail(sph_system* s, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;  va_start(ap, fmt);  vsnprintf(buf, sizeof buf, fmt, ap);  va_end(ap);
+    if (s) s->err = buf; else g_createError = buf;
+    return code;
+}
+
+#define CU_TRY(s, call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail((s), SPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static const char* check_params(const SimParams* p)
+{
+    if (p->numParticles == 0) return "numParticles is 0";
+    if (p->gridSize.x < 4 || p->gridSize.y < 4 || p->gridSize.z < 4)
+        return "every grid dimension must be >= 4 cells (SURVEY.md Q3: unclamped neighbour hashes must miss)";
+    if ((unsigned long long)p->gridSize.x * p->gridSize.y != p->gridSize_yx) return "gridSize_yx != gridSize.y*gridSize.x";
+    if ((unsigned long long)p->gridSize_yx * p->gridSize.z != p->numCells) return "numCells != gridSize.x*y*z";
+    if (p->numCells > 0x7fffff00u) return "numCells too large";
+    if (p->iHmap > 0) return "height-map obstacles (iHmap>0) are not implemented yet";
+    if (p->rotType > 0) return "rotor obstacles (rotType>0) are not implemented yet";
+    return nullptr;
+}
+
+static SphLaunch launcher(sph_system* s) { SphLaunch L;  L.stream = s->stream;  L.launches = &s->launches;  return L; }
+
+template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+
+extern "C" const char* sph_version(void) { return "pibiti_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* sph_last_error(sph_t* s) { return s ? s->err.c_str() : g_createError.c_str(); }
+
+extern "C" int sph_destroy(sph_t* s)
+{
+    if (!s) return SPH_ERR_ARG;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
+                    s->rankU, s->keyS, s->counts, s->pairT, s->cellCount, s->cellStart, s->tileSums, s->maxCount};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return SPH_OK;
+}
+
+extern "C" int sph_create(const struct SimParams* params, int device, sph_t** out)
+{
+    if (!params || !out) return fail(nullptr, SPH_ERR_ARG, "sph_create: null argument");
+    *out = nullptr;
+    if (const char* why = check_params(params)) return fail(nullptr, SPH_ERR_PARAMS, "sph_create: %s", why);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SPH_ERR_CUDA, "sph_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, SPH_ERR_ARG, "sph_create: device %d out of range", device);
+    cudaDeviceProp prop;
+    CU_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SPH_ERR_CUDA, "sph_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    CU_TRY(nullptr, cudaSetDevice(device));
+
+    sph_system* s = new sph_system();
+    s->device = device;
+    s->par = *params;
+    const size_t n = params->numParticles, C = params->numCells;
+    s->nAlloc = (int)n;  s->cellsAlloc = (int)C;
+    const size_t tiles = (C + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
+
+#define ALLOC(ptr, count)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = dalloc(&(ptr), (count));                                                      \
+        if (_e != cudaSuccess) {                                                                       \
+            int rc = fail(nullptr, SPH_ERR_CUDA, "sph_create: cudaMalloc(%s, %zu) failed: %s", #ptr,   \
+                          (size_t)(count), cudaGetErrorString(_e));                                    \
+            sph_destroy(s);                                                                            \
+            return rc;                                                                                 \
+        }                                                                                              \
+    } while (0)
+
+    ALLOC(s->pos[0], n);  ALLOC(s->pos[1], n);  ALLOC(s->vel, n);  ALLOC(s->velS, n);
+    ALLOC(s->posP, n);    ALLOC(s->velD, n);    ALLOC(s->io, n);
+    ALLOC(s->idx[0], n);  ALLOC(s->idx[1], n);  ALLOC(s->keyU, n);  ALLOC(s->rankU, n);  ALLOC(s->keyS, n);
+    ALLOC(s->counts, n);  ALLOC(s->pairT, n);
+    ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
+#undef ALLOC
+
+    CU_TRY(nullptr, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& ev : s->ev) CU_TRY(nullptr, cudaEventCreate(&ev));
+
+    sph_pair_default_config(&s->cfgDensity, &s->cfgForce);
+    if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "threads,capDensity,capForce" -- tuning aid
+        int t = 0, cd = 0, cf = 0;
+        if (sscanf(env, "%d,%d,%d", &t, &cd, &cf) == 3 && t >= 32 && t <= 256 && cd > 0 && cf > 0) {
+            s->cfgDensity.threads = s->cfgForce.threads = t;  s->cfgDensity.cap = cd;  s->cfgForce.cap = cf;
+        }
+    }
+    CU_TRY(nullptr, sph_pair_prepare(s->cfgDensity, s->cfgForce));
+
+    CU_TRY(nullptr, cudaMemsetAsync(s->pos[0], 0, n * sizeof(float4), s->stream));
+    CU_TRY(nullptr, cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
+    CU_TRY(nullptr, cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
+    CU_TRY(nullptr, cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
+    sph_launch_iota(launcher(s), s->idx[0], (int)n);
+    CU_TRY(nullptr, cudaStreamSynchronize(s->stream));
+    *out = s;
+    return SPH_OK;
+}
+
+extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
+{
+    if (!s || !p) return SPH_ERR_ARG;
+    if (const char* why = check_params(p)) return fail(s, SPH_ERR_PARAMS, "sph_set_params: %s", why);
+    if ((int)p->numParticles > s->nAlloc || (int)p->numCells > s->cellsAlloc)
+        return fail(s, SPH_ERR_PARAMS, "sph_set_params: numParticles/numCells exceed the allocation of sph_create");
+    if (p->numCells != s->par.numCells || p->numParticles != s->par.numParticles) s->stepped = false;
+    s->par = *p;
+    return SPH_OK;
+}
+
+extern "C" int sph_get_params(sph_t* s, struct SimParams* out)
+{
+    if (!s || !out) return SPH_ERR_ARG;
+    *out = s->par;
+    return SPH_OK;
+}
+
+extern "C" int sph_step(sph_t* s, int nsteps)
+{
+    if (!s || nsteps < 0) return SPH_ERR_ARG;
+    CU_TRY(s, cudaSetDevice(s->device));
+    const int n = (int)s->par.numParticles, C = (int)s->par.numCells;
+    SphLaunch L = launcher(s);
+    for (int it = 0; it < nsteps; it++) {
+        const bool tm = s->timing && it == nsteps - 1;
+        const int in = s->cur, outb = s->cur ^ 1;
+        if (tm) cudaEventRecord(s->ev[0], s->stream);
+        sph_launch_integrate_hash(L, s->par, s->pos[in], s->vel, s->keyU, s->rankU, s->cellCount, n);
+        if (tm) cudaEventRecord(s->ev[1], s->stream);
+        sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, C);
+        sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, n);
+        if (tm) cudaEventRecord(s->ev[2], s->stream);
+        sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel,
+                               s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
+        if (tm) cudaEventRecord(s->ev[3], s->stream);
+        sph_launch_density(L, s->cfgDensity, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
+                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, n);
+        if (tm) cudaEventRecord(s->ev[4], s->stream);
+        sph_launch_force(L, s->cfgForce, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
+                         s->vel, n);
+        if (tm) cudaEventRecord(s->ev[5], s->stream);
+        s->cur = outb;
+        s->stepped = true;
+    }
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_sync(sph_t* s)
+{
+    if (!s) return SPH_ERR_ARG;
+    CU_TRY(s, cudaSetDevice(s->device));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return SPH_OK;
+}
+
+static int check_range(sph_system* s, int start, int count)
+{
+    if (start < 0 || count < 0 || (long long)start + count > (long long)s->par.numParticles)
+        return fail(s, SPH_ERR_ARG, "particle range [%d,%d) outside [0,%u)", start, start + count, s->par.numParticles);
+    return SPH_OK;
+}
+
+extern "C" int sph_set_array_device(sph_t* s, int which, const float* d_xyzw, int start, int count)
+{
+    if (!s || !d_xyzw) return SPH_ERR_ARG;
+    if (int rc = check_range(s, start, count)) return rc;
+    if (which != SPH_POS && which != SPH_VEL) return fail(s, SPH_ERR_ARG, "sph_set_array: only SPH_POS / SPH_VEL can be written");
+    CU_TRY(s, cudaSetDevice(s->device));
+    float4* dst = which == SPH_POS ? s->pos[s->cur] : s->vel;
+    sph_launch_permute4(launcher(s), dst, s->idx[s->cur], (const float4*)d_xyzw, start, count, (int)s->par.numParticles);
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_set_array(sph_t* s, int which, const float* xyzw, int start, int count)
+{
+    if (!s || !xyzw) return SPH_ERR_ARG;
+    if (int rc = check_range(s, start, count)) return rc;
+    CU_TRY(s, cudaSetDevice(s->device));
+    CU_TRY(s, cudaMemcpyAsync(s->io, xyzw, (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    int rc = sph_set_array_device(s, which, (const float*)s->io, start, count);
+    // the staging buffer is reused by the next call: finish before returning (the reference's
+    // setArray is a blocking glBufferSubData / cudaMemcpy as well)
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return rc;
+}
+
+extern "C" int sph_get_array_device(sph_t* s, int which, float* d_out, int start, int count)
+{
+    if (!s || !d_out) return SPH_ERR_ARG;
+    if (int rc = check_range(s, start, count)) return rc;
+    CU_TRY(s, cudaSetDevice(s->device));
+    const int n = (int)s->par.numParticles;
+    SphLaunch L = launcher(s);
+    switch (which) {
+    case SPH_POS: sph_launch_unpermute4(L, s->pos[s->cur], s->idx[s->cur], (float4*)d_out, start, count, n); break;
+    case SPH_VEL: sph_launch_unpermute4(L, s->vel, s->idx[s->cur], (float4*)d_out, start, count, n); break;
+    case SPH_DENSITY:
+        if (!s->stepped) return fail(s, SPH_ERR_STATE, "density is only defined after a step");
+        sph_launch_unpermute_w(L, s->velD, s->idx[s->cur], d_out, start, count, n); break;
+    case SPH_PRESSURE:
+        if (!s->stepped) return fail(s, SPH_ERR_STATE, "pressure is only defined after a step");
+        sph_launch_unpermute_w(L, s->posP, s->idx[s->cur], d_out, start, count, n); break;
+    default: return fail(s, SPH_ERR_ARG, "sph_get_array: array %d not available", which);
+    }
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_get_array(sph_t* s, int which, float* out, int start, int count)
+{
+    if (!s || !out) return SPH_ERR_ARG;
+    int rc = sph_get_array_device(s, which, (float*)s->io, start, count);
+    if (rc) return rc;
+    size_t elem = (which == SPH_POS || which == SPH_VEL || which == SPH_COLOR) ? sizeof(float4) : sizeof(float);
+    CU_TRY(s, cudaMemcpyAsync(out, s->io, (size_t)count * elem, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return SPH_OK;
+}
+
+extern "C" int sph_device_buffers(sph_t* s, const float** d_pos, const float** d_vel, const uint32_t** d_index,
+                                  const uint32_t** d_cellStart)
+{
+    if (!s) return SPH_ERR_ARG;
+    if (d_pos) *d_pos = (const float*)s->pos[s->cur];
+    if (d_vel) *d_vel = (const float*)s->vel;
+    if (d_index) *d_index = s->idx[s->cur];
+    if (d_cellStart) *d_cellStart = s->stepped ? s->cellStart : nullptr;
+    return SPH_OK;
+}
+
+extern "C" int sph_debug_dump(sph_t* s, int what, void* out, size_t outBytes)
+{
+    if (!s || !out) return SPH_ERR_ARG;
+    if (!s->stepped) return fail(s, SPH_ERR_STATE, "sph_debug_dump: no step has run yet");
+    CU_TRY(s, cudaSetDevice(s->device));
+    const size_t n = s->par.numParticles, C = s->par.numCells;
+    SphLaunch L = launcher(s);
+    const void* src = nullptr;  size_t bytes = 0;
+    std::vector<float> tmp;
+    switch (what) {
+    case SPH_DUMP_SORTED_PAIRS:
+        sph_launch_pack_pairs(L, s->keyS, s->idx[s->cur], s->pairT, (int)n);
+        src = s->pairT;  bytes = n * 8;  break;
+    case SPH_DUMP_CELL_START:
+    case SPH_DUMP_CELL_END:
+        // cellCount is all zeros between steps: borrow it as the output buffer and re-zero it afterwards
+        sph_launch_cell_table_dump(L, s->cellStart, what == SPH_DUMP_CELL_START ? s->cellCount : nullptr,
+                                   what == SPH_DUMP_CELL_END ? s->cellCount : nullptr, (int)C);
+        src = s->cellCount;  bytes = C * 4;  break;
+    case SPH_DUMP_SORTED_POS: src = s->pos[s->cur];  bytes = n * 16;  break;
+    case SPH_DUMP_SORTED_VEL: src = s->velS;  bytes = n * 16;  break;
+    case SPH_DUMP_PRESSURE:
+    case SPH_DUMP_DENSITY: {
+        if (outBytes < n * 4) return fail(s, SPH_ERR_ARG, "sph_debug_dump: output buffer too small");
+        tmp.resize(4 * n);
+        CU_TRY(s, cudaMemcpyAsync(tmp.data(), what == SPH_DUMP_PRESSURE ? s->posP : s->velD, n * 16,
+                                  cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(s, cudaStreamSynchronize(s->stream));
+        float* o = (float*)out;
+        for (size_t i = 0; i < n; i++) o[i] = tmp[4 * i + 3];
+        return SPH_OK;
+    }
+    case SPH_DUMP_NEIGHBOR_COUNTS:
+        // recompute density on the sorted state with counting enabled (same kernel, COUNT=true)
+        sph_launch_density(L, s->cfgDensity, s->par, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount,
+                           s->posP, s->velD, s->counts, (int)n);
+        src = s->counts;  bytes = n * 4;  break;
+    default: return fail(s, SPH_ERR_ARG, "sph_debug_dump: unknown item %d", what);
+    }
+    if (outBytes < bytes) return fail(s, SPH_ERR_ARG, "sph_debug_dump: output buffer too small (%zu < %zu)", outBytes, bytes);
+    CU_TRY(s, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (what == SPH_DUMP_CELL_START || what == SPH_DUMP_CELL_END)
+        CU_TRY(s, cudaMemsetAsync(s->cellCount, 0, C * 4, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_get_timings(sph_t* s, float* msPerStage, int enable)
+{
+    if (!s) return SPH_ERR_ARG;
+    if (msPerStage && s->timing && s->stepped) {
+        CU_TRY(s, cudaSetDevice(s->device));
+        CU_TRY(s, cudaStreamSynchronize(s->stream));
+        for (int k = 0; k < SPH_STAGE_COUNT; k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+            msPerStage[k] = ms;
+        }
+    } else if (msPerStage) {
+        for (int k = 0; k < SPH_STAGE_COUNT; k++) msPerStage[k] = -1.f;
+    }
+    s->timing = enable != 0;
+    return SPH_OK;
+}
+
+extern "C" int sph_kernel_launch_count(sph_t* s, long long* launches)
+{
+    if (!s || !launches) return SPH_ERR_ARG;
+    *launches = s->launches;
+    return SPH_OK;
+}
+
+extern "C" void* sph_cuda_stream(sph_t* s) { return s ? (void*)s->stream : nullptr; }

@@ -1,0 +1,56 @@
+// sph_device.cuh -- declarations shared by the kernel translation units and the C ABI.
+//
+// Data layout in HBM (n = numParticles, C = numCells), all in "slot order" = the sorted order
+// of the last completed step:
+//   pos[2]   float4[n]  ping-pong: the live positions are gathered into the other buffer by reorder
+//   vel      float4[n]  live velocities (integrate in place; force writes the new ones here)
+//   velS     float4[n]  post-integration velocities in sorted order (reference dSortedVel)
+//   idx[2]   u32[n]     original particle index of each slot (ping-pong with pos)
+//   keyU     u32[n]     cell hash of each slot after integrate (unsorted)
+//   rankU    u32[n]     arrival rank inside its cell (from the histogram atomic)
+//   pairT    uint2[n]   (source slot, original index) bucketed by cell, arbitrary order inside a cell
+//   keyS     u32[n]     cell hash in sorted order
+//   posP     float4[n]  (x, y, z, pressure) sorted  -- written by density, read by force
+//   velD     float4[n]  (vx, vy, vz, density) sorted -- written by density, read by force
+//   cellCount u32[C]    histogram, zeroed again by the scan
+//   cellStart u32[C+1]  exclusive scan: cell c owns sorted slots [cellStart[c], cellStart[c+1])
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sph_params.h"
+
+#define SPH_SCAN_TILE 4096          // cells per scan block (256 threads x 16)
+
+struct SphLaunch {
+    cudaStream_t stream;
+    long long* launches;            // counter of kernels launched (host side)
+};
+
+// ---- sph_stream_kernels.cu (compiled with -fmad=false: bit-exact vs the CPU oracle) ----------
+void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel,
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n);
+void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* blockSums,
+                     uint32_t* maxCount, int numCells);
+void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
+                       const uint32_t* cellStart, uint2* pairT, int n);
+void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
+                            const float4* posIn, const float4* velIn,
+                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n);
+void sph_launch_iota(const SphLaunch& L, uint32_t* idx, int n);
+// original-order accessors: out[idx[j] - start] = src[j]  /  dst[j] = in[idx[j] - start]
+void sph_launch_unpermute4(const SphLaunch& L, const float4* src, const uint32_t* idx, float4* out, int start, int count, int n);
+void sph_launch_unpermute_w(const SphLaunch& L, const float4* src, const uint32_t* idx, float* out, int start, int count, int n);
+void sph_launch_permute4(const SphLaunch& L, float4* dst, const uint32_t* idx, const float4* in, int start, int count, int n);
+void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, uint32_t* outStart, uint32_t* outEnd, int numCells);
+void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n);
+
+// ---- sph_pair_kernels.cu ----------------------------------------------------------------------
+struct SphPairConfig { int threads; int cap; };     // CTA size and staged-candidate capacity
+void sph_pair_default_config(SphPairConfig* density, SphPairConfig* force);
+cudaError_t sph_pair_prepare(const SphPairConfig& density, const SphPairConfig& force);
+void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
+                        const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
+                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts, int n);
+void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
+                      const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
+                      const uint32_t* cellStart, const uint32_t* maxCount, float4* velOut, int n);

@@ -1,0 +1,440 @@
+// sph_pair_kernels.cu -- density/pressure and pair-force kernels for sm_100a.
+//
+// One CTA owns a run of consecutive SORTED particles.  Because the cell hash is linear and z-major
+// (reference Kernel_Cell.cui:15-19), the 3x3x3 neighbourhood of that run is nine contiguous ranges
+// of the sorted arrays -- one per (dy,dz) grid row -- so the whole candidate set is staged into
+// shared memory by at most nine 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on
+// one mbarrier; float4 elements keep every source offset 16-byte aligned.  Overlapping ranges are
+// merged first so no candidate is staged twice.  Each thread then walks, for its own particle, the
+// nine 3-cell runs [cellStart[h-1], cellStart[h+2]) out of shared memory.
+//
+// Reference semantics kept:
+//   * search radius is always +-1 cell, cells are addressed by unclamped hash arithmetic, and
+//     hashes outside [0,numCells) contribute nothing (Kernel_Cell.cui:146-155);
+//   * at most maxParInCell entries of a cell are visited (Kernel_Cell.cui:151,245).  The scan
+//     records the largest cell; only if it exceeds maxParInCell do the kernels take the per-cell
+//     truncating walk, otherwise three cells are walked as one run;
+//   * density: sum (h2-r2)^3 over r2<h2, j!=i; rho = sum*Poly6*mass; p = (rho-rho0)*k
+//     (Kernel_Cell.cui:142-199).  The r2<h2 predicate is evaluated without FMA contraction so the
+//     neighbour set is bit-identical to the CPU oracle's;
+//   * force: compForcePair / compForceCell (Kernel_Cell.cui:210-261), then F*mass*dt, sphere
+//     collider, accelerators, newVel = vel + dv (System.cu:247-250,373-402).
+#include "sph_device.cuh"
+
+namespace {
+
+constexpr int kRows = 9;
+
+struct StageTable {
+    uint32_t g0[kRows], g1[kRows];          // clipped sorted-index range of each (dy,dz) row
+    int      segOf[kRows];                  // row -> merged segment (or -1)
+    uint32_t segG0[kRows], segG1[kRows];    // merged segment: global range
+    uint32_t segS0[kRows];                  // merged segment: first shared-memory slot
+    int      nseg;
+    uint32_t total;                         // staged candidates
+    int      staged;                        // 0: candidate set larger than the staging buffer
+    unsigned long long bar;                 // mbarrier
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!done);
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dstSmem, const void* srcGlobal, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Threads 0..8 look up the nine row ranges; thread 0 merges them and issues the bulk copies.
+// Returns after a __syncthreads with st filled in.  NARR arrays of float4 are staged back to back
+// (array a occupies slots [a*cap, a*cap+total)).
+template <int NARR>
+__device__ __forceinline__ void stage_candidates(StageTable& st, float4* sbuf, int cap, const SimParams& par,
+                                                 const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart,
+                                                 const float4* __restrict__ arr0, const float4* __restrict__ arr1,
+                                                 int p0, int p1)
+{
+    const int tid = threadIdx.x;
+    if (tid < kRows) {
+        const long long kLo = keyS[p0], kHi = keyS[p1 - 1];
+        const int dz = tid / 3 - 1, dy = tid % 3 - 1;
+        const long long off = (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
+        long long lo = kLo + off - 1, hi = kHi + off + 1;
+        if (lo < 0) lo = 0;
+        if (hi > (long long)par.numCells - 1) hi = (long long)par.numCells - 1;
+        uint32_t a = 0, e = 0;
+        if (lo <= hi) { a = __ldg(cellStart + lo); e = __ldg(cellStart + hi + 1); }
+        st.g0[tid] = a;  st.g1[tid] = e;
+    }
+    if (tid == 0) mbar_init(&st.bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        int nseg = 0;  uint32_t total = 0;
+        for (int r = 0; r < kRows; r++) {
+            uint32_t a = st.g0[r], e = st.g1[r];
+            if (e <= a) { st.segOf[r] = -1; continue; }
+            if (nseg > 0 && a <= st.segG1[nseg - 1]) {
+                if (e > st.segG1[nseg - 1]) st.segG1[nseg - 1] = e;
+            } else {
+                st.segG0[nseg] = a;  st.segG1[nseg] = e;  nseg++;
+            }
+            st.segOf[r] = nseg - 1;
+        }
+        for (int s = 0; s < nseg; s++) { st.segS0[s] = total;  total += st.segG1[s] - st.segG0[s]; }
+        st.nseg = nseg;  st.total = total;
+        st.staged = (total <= (uint32_t)cap) ? 1 : 0;
+        if (st.staged && total > 0) {
+            mbar_expect_tx(&st.bar, total * 16u * NARR);
+            for (int s = 0; s < nseg; s++) {
+                uint32_t len = st.segG1[s] - st.segG0[s];
+                tma_bulk_g2s(sbuf + st.segS0[s], arr0 + st.segG0[s], len * 16u, &st.bar);
+                if (NARR > 1) tma_bulk_g2s(sbuf + cap + st.segS0[s], arr1 + st.segG0[s], len * 16u, &st.bar);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- density -------------------------------------------------------------------------------------
+
+// r2 exactly as the CPU evaluates "p.x*p.x + p.y*p.y + p.z*p.z" (no contraction)
+__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void density_span(const float4* __restrict__ cand, uint32_t a, uint32_t e,
+                                             float3 pi, float h2, float& sum, uint32_t& cnt)
+{
+    #pragma unroll 4
+    for (uint32_t g = a; g < e; g++) {
+        float4 q = cand[g];
+        float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
+        if (r2 < h2) {
+            float c = h2 - r2;
+            sum += c * c * c;
+            if (COUNT) cnt++;
+        }
+    }
+}
+
+// walk [a,e) of the sorted order skipping self; `cand` is indexed by (sorted index + shift)
+template <bool COUNT>
+__device__ __forceinline__ void density_run(const float4* __restrict__ cand, int shift, uint32_t a, uint32_t e,
+                                            uint32_t self, float3 pi, float h2, float& sum, uint32_t& cnt)
+{
+    const float4* c = cand + shift;
+    if (self - a < e - a) {
+        density_span<COUNT>(c, a, self, pi, h2, sum, cnt);
+        density_span<COUNT>(c, self + 1, e, pi, h2, sum, cnt);
+    } else {
+        density_span<COUNT>(c, a, e, pi, h2, sum, cnt);
+    }
+}
+
+template <bool STAGED, bool COUNT>
+__device__ __forceinline__ void density_particle(const StageTable& st, const float4* __restrict__ sbuf,
+                                                 const float4* __restrict__ posS, const uint32_t* __restrict__ cellStart,
+                                                 const SimParams& par, bool trunc, uint32_t i, uint32_t key, float3 pi,
+                                                 float& sum, uint32_t& cnt)
+{
+    const float h2 = par.h2;
+    const long long C = par.numCells;
+    #pragma unroll 1
+    for (int r = 0; r < kRows; r++) {
+        const int dz = r / 3 - 1, dy = r % 3 - 1;
+        const long long hb = (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
+        const float4* cand;  int shift;
+        if (STAGED) {
+            int sg = st.segOf[r];
+            if (sg < 0) continue;
+            cand = sbuf;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
+        } else { cand = posS;  shift = 0; }
+        if (!trunc) {
+            long long lo = hb - 1, hi = hb + 1;
+            if (lo < 0) lo = 0;
+            if (hi > C - 1) hi = C - 1;
+            if (lo > hi) continue;
+            uint32_t a = __ldg(cellStart + lo), e = __ldg(cellStart + hi + 1);
+            density_run<COUNT>(cand, shift, a, e, i, pi, h2, sum, cnt);
+        } else {
+            for (int x = -1; x <= 1; x++) {
+                long long h = hb + x;
+                if (h < 0 || h >= C) continue;
+                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
+                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
+                density_run<COUNT>(cand, shift, a, e, i, pi, h2, sum, cnt);
+            }
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_density(const __grid_constant__ SimParams par, int cap,
+          const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
+          const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+          float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts, int n)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    float4* sbuf = reinterpret_cast<float4*>(smemRaw);
+    __shared__ StageTable st;
+
+    const int p0 = blockIdx.x * blockDim.x;
+    const int p1 = min(n, p0 + (int)blockDim.x);
+    stage_candidates<1>(st, sbuf, cap, par, keyS, cellStart, posS, nullptr, p0, p1);
+
+    const int i = p0 + threadIdx.x;
+    if (i >= p1) return;
+    const float4 p4 = posS[i];
+    const float4 v4 = velS[i];
+    const uint32_t key = keyS[i];
+    const bool trunc = __ldg(maxCount) > par.maxParInCell;
+    const float3 pi = make_float3(p4.x, p4.y, p4.z);
+
+    float sum = 0.f;  uint32_t cnt = 0;
+    if (st.staged) {
+        if (st.total > 0) mbar_wait(&st.bar, 0);
+        density_particle<true, COUNT>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt);
+    } else {
+        density_particle<false, COUNT>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt);
+    }
+
+    const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
+    const float pres = (dens - par.restDensity) * par.stiffness;
+    posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
+    velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
+    if (COUNT) neighborCounts[i] = cnt;
+}
+
+// ---- force ---------------------------------------------------------------------------------------
+
+struct ForceConsts { float h, minDist, spiky, vterm, minDens; };
+
+__device__ __forceinline__ void force_span(const float4* __restrict__ cpp, const float4* __restrict__ cvd,
+                                           uint32_t a, uint32_t e, float3 pi, float3 vi, float presI, float densI,
+                                           const ForceConsts& k, float3& f)
+{
+    #pragma unroll 2
+    for (uint32_t g = a; g < e; g++) {
+        float4 q = cpp[g];
+        float dx = pi.x - q.x, dy = pi.y - q.y, dz = pi.z - q.z;
+        float r = fmaxf(k.minDist, sqrtf(dx * dx + dy * dy + dz * dz));
+        if (r < k.h) {
+            float4 u = cvd[g];
+            float c = k.h - r;
+            float pterm = c * k.spiky * (presI + q.w) / r;
+            float d12 = fminf(k.minDens, 1.0f / (densI * u.w));
+            float s = c * d12;
+            f.x += (pterm * dx + k.vterm * (u.x - vi.x)) * s;
+            f.y += (pterm * dy + k.vterm * (u.y - vi.y)) * s;
+            f.z += (pterm * dz + k.vterm * (u.z - vi.z)) * s;
+        }
+    }
+}
+
+__device__ __forceinline__ void force_run(const float4* __restrict__ cpp, const float4* __restrict__ cvd, int shift,
+                                          uint32_t a, uint32_t e, uint32_t self, float3 pi, float3 vi,
+                                          float presI, float densI, const ForceConsts& k, float3& f)
+{
+    const float4* c0 = cpp + shift;
+    const float4* c1 = cvd + shift;
+    if (self - a < e - a) {
+        force_span(c0, c1, a, self, pi, vi, presI, densI, k, f);
+        force_span(c0, c1, self + 1, e, pi, vi, presI, densI, k, f);
+    } else {
+        force_span(c0, c1, a, e, pi, vi, presI, densI, k, f);
+    }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ float3 force_particle(const StageTable& st, const float4* __restrict__ sbuf, int cap,
+                                                 const float4* __restrict__ posP, const float4* __restrict__ velD,
+                                                 const uint32_t* __restrict__ cellStart, const SimParams& par, bool trunc,
+                                                 uint32_t i, uint32_t key, float4 pp, float4 vd)
+{
+    ForceConsts k;
+    k.h = par.h;  k.minDist = par.minDist;  k.spiky = par.SpikyKern;
+    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
+    const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+    const long long C = par.numCells;
+    float3 f = make_float3(0.f, 0.f, 0.f);
+    #pragma unroll 1
+    for (int r = 0; r < kRows; r++) {
+        const int dz = r / 3 - 1, dy = r % 3 - 1;
+        const long long hb = (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
+        const float4 *c0, *c1;  int shift;
+        if (STAGED) {
+            int sg = st.segOf[r];
+            if (sg < 0) continue;
+            c0 = sbuf;  c1 = sbuf + cap;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
+        } else { c0 = posP;  c1 = velD;  shift = 0; }
+        if (!trunc) {
+            long long lo = hb - 1, hi = hb + 1;
+            if (lo < 0) lo = 0;
+            if (hi > C - 1) hi = C - 1;
+            if (lo > hi) continue;
+            uint32_t a = __ldg(cellStart + lo), e = __ldg(cellStart + hi + 1);
+            force_run(c0, c1, shift, a, e, i, pi, vi, pp.w, vd.w, k, f);
+        } else {
+            for (int x = -1; x <= 1; x++) {
+                long long h = hb + x;
+                if (h < 0 || h >= C) continue;
+                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
+                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
+                force_run(c0, c1, shift, a, e, i, pi, vi, pp.w, vd.w, k, f);
+            }
+        }
+    }
+    return f;
+}
+
+// DEM sphere contact (Kernel_Cell.cui:78-96): relPos/relVel are collider minus particle
+__device__ __forceinline__ float3 sphere_contact(const SimParams& par, float3 relPos, float3 relVel, float radiusAB)
+{
+    float dist = sqrtf(relPos.x * relPos.x + relPos.y * relPos.y + relPos.z * relPos.z);
+    float3 force = make_float3(0.f, 0.f, 0.f);
+    if (dist < radiusAB) {
+        float inv = 1.0f / dist;
+        float3 nrm = make_float3(relPos.x * inv, relPos.y * inv, relPos.z * inv);
+        float dn = relVel.x * nrm.x + relVel.y * nrm.y + relVel.z * nrm.z;
+        float3 tanVel = make_float3(relVel.x - dn * nrm.x, relVel.y - dn * nrm.y, relVel.z - dn * nrm.z);
+        float sp = par.spring * (dist - radiusAB);
+        force.x = sp * nrm.x + par.damping * relVel.x + par.shear * tanVel.x;
+        force.y = sp * nrm.y + par.damping * relVel.y + par.shear * tanVel.y;
+        force.z = sp * nrm.z + par.damping * relVel.z + par.shear * tanVel.z;
+    }
+    return force;
+}
+
+__global__ void __launch_bounds__(256)
+k_force(const __grid_constant__ SimParams par, int cap,
+        const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
+        const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+        float4* __restrict__ velOut, int n)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    float4* sbuf = reinterpret_cast<float4*>(smemRaw);
+    __shared__ StageTable st;
+
+    const int p0 = blockIdx.x * blockDim.x;
+    const int p1 = min(n, p0 + (int)blockDim.x);
+    stage_candidates<2>(st, sbuf, cap, par, keyS, cellStart, posP, velD, p0, p1);
+
+    const int i = p0 + threadIdx.x;
+    if (i >= p1) return;
+    const float4 pp = posP[i];
+    const float4 vd = velD[i];
+    const float velW = velS[i].w;
+    const uint32_t key = keyS[i];
+    const bool trunc = __ldg(maxCount) > par.maxParInCell;
+
+    float3 f;
+    if (st.staged) {
+        if (st.total > 0) mbar_wait(&st.bar, 0);
+        f = force_particle<true>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd);
+    } else {
+        f = force_particle<false>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd);
+    }
+
+    const float md = par.particleMass * par.timeStep;                     // System.cu:250
+    float3 dv = make_float3(f.x * md, f.y * md, f.z * md);
+
+    if (par.rotType == 0) {                                               // System.cu:373-375
+        float3 c = sphere_contact(par, make_float3(par.collPos.x - pp.x, par.collPos.y - pp.y, par.collPos.z - pp.z),
+                                  make_float3(-vd.x, -vd.y, -vd.z), par.particleR + par.collR);
+        dv.x += c.x;  dv.y += c.y;  dv.z += c.z;
+    }
+
+    #pragma unroll
+    for (int a = 0; a < SPH_NUM_ACC; a++) {                               // System.cu:379-399
+        const Accel& ac = par.acc[a];
+        if (ac.type == ACC_Off) continue;
+        float3 rel = make_float3(pp.x - ac.pos.x, pp.y - ac.pos.y, pp.z - ac.pos.z);
+        if (ac.type == ACC_Box) {
+            if (fabsf(rel.x) < ac.size.x && fabsf(rel.y) < ac.size.y && fabsf(rel.z) < ac.size.z) {
+                dv.x += ac.acc.x * par.timeStep;  dv.y += ac.acc.y * par.timeStep;  dv.z += ac.acc.z * par.timeStep;
+            }
+        } else if (ac.type == ACC_CylY) {
+            float ex = rel.x / ac.size.x, ez = rel.z / ac.size.z;
+            float rr = sqrtf(ex * ex + ez * ez);
+            if (fabsf(rel.y) < ac.size.y && rr < 1.f) {
+                dv.x += ac.acc.x * par.timeStep;  dv.y += ac.acc.y * par.timeStep;  dv.z += ac.acc.z * par.timeStep;
+            }
+        } else if (ac.type == ACC_CylYsm) {
+            float rr = sqrtf(rel.x * rel.x + rel.z * rel.z);
+            if (fabsf(rel.y) < ac.size.y && rr < ac.size.x) {
+                dv.x += ac.acc.x * (1.f - rr / ac.size.z) * par.timeStep;
+                dv.y += ac.acc.y * (1.f - rr / ac.size.z) * par.timeStep;
+                dv.z += ac.acc.z * (1.f - rr / ac.size.z) * par.timeStep;
+            }
+        }
+    }
+
+    velOut[i] = make_float4(vd.x + dv.x, vd.y + dv.y, vd.z + dv.z, velW + 0.0f);   // System.cu:402
+}
+
+}  // namespace
+
+#define SPH_COUNT(L) do { if ((L).launches) ++*(L).launches; } while (0)
+
+void sph_pair_default_config(SphPairConfig* density, SphPairConfig* force)
+{
+    density->threads = 128;  density->cap = 1536;
+    force->threads = 128;    force->cap = 1536;
+}
+
+cudaError_t sph_pair_prepare(const SphPairConfig& d, const SphPairConfig& f)
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.cap * 16);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.cap * 16);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, f.cap * 32);
+}
+
+void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
+                        const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
+                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts, int n)
+{
+    int blocks = (n + cfg.threads - 1) / cfg.threads;
+    size_t smem = (size_t)cfg.cap * 16;
+    if (neighborCounts)
+        k_density<true><<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount, posP, velD, neighborCounts, n);
+    else
+        k_density<false><<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount, posP, velD, nullptr, n);
+    SPH_COUNT(L);
+}
+
+void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
+                      const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
+                      const uint32_t* cellStart, const uint32_t* maxCount, float4* velOut, int n)
+{
+    int blocks = (n + cfg.threads - 1) / cfg.threads;
+    size_t smem = (size_t)cfg.cap * 32;
+    k_force<<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount, velOut, n);
+    SPH_COUNT(L);
+}

@@ -1,0 +1,481 @@
+// sph_stream_kernels.cu -- the HBM-streaming stages of the SPH step for sm_100a:
+//   integrate + boundary + cell hash + cell histogram   (one pass, 72 B/particle)
+//   cell-table exclusive scan                            (8 B/cell)
+//   deterministic stable counting sort + reorder         (bucket, then rank-by-index + gather)
+//   original-order accessors
+//
+// Built with -fmad=false: every float expression here is evaluated with the same IEEE
+// operations, in the same order, as the reference source evaluates them when it is compiled for
+// a CPU (which is what the parity oracle is).  That makes positions, velocities and therefore
+// cell hashes bit-exact against the oracle for every boundary type that uses no libm call.
+// These kernels are HBM-bound; the extra multiplies cost nothing.
+//
+// Reference behaviour restated here (nothing is copied; see DESIGN.md for the mapping):
+//   boundary()            source/CUDA/System.cu:41-159
+//   integrateD            source/CUDA/System.cu:165-205
+//   calcGridPos/Hash      source/CUDA/Kernel_Cell.cui:5-19
+//   RadixSort + reorderD  source/CUDA/radixsort_kernel.cu:445-472, Kernel_Cell.cui:40-67
+#include "sph_device.cuh"
+
+namespace {
+
+constexpr float kBndEps = 0.00001f;      // System.cu:51
+
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// One soft-wall impulse:  acc = stiff*diff - damp*(n.v);  v += acc*n*dt      (System.cu:52-53)
+__device__ __forceinline__ void wall_push(float3& v, float3 n, float diff, float stiff, float damp, float dt)
+{
+    float acc = stiff * diff - damp * dot3(n, v);
+    v.x += (acc * n.x) * dt;
+    v.y += (acc * n.y) * dt;
+    v.z += (acc * n.z) * dt;
+}
+
+struct BoundaryCtx {
+    float waveShift;        // rTwist*(1+sinf(rAngle)), evaluated on the host so that it is the same
+                            // libm result the CPU oracle sees (System.cu:60)
+};
+
+// Soft penalty boundaries.  pos may be teleported (wrap / cycle / pump exit).
+__device__ __forceinline__ void soft_boundary(const SimParams& par, const BoundaryCtx& ctx, float3& pos, float3& vel)
+{
+    float3 wmin = par.worldMin, wmax = par.worldMax;
+    const float b = par.distBndSoft, stiff = par.bndStiff, dampB = par.bndDamp, dampC = par.bndDampC;
+    const float dt = par.timeStep;
+    const BndType t = par.bndType;
+    const bool cylY = t == BND_CYL_Y, cylZ = t == BND_CYL_Z;
+    const bool wave = par.bndEffZ == BND_EFF_WAVE, noEff = par.bndEffZ == BND_EFF_NONE,
+               cycle = par.bndEffZ == BND_EFF_CYCLE;
+    float diff;
+
+    if (wave) {                                                     // System.cu:55-61
+        float sl = -par.r2Angle;
+        diff = b - (pos.y - wmin.y) - (pos.z - wmin.z) * sl;
+        if (diff > kBndEps) wall_push(vel, make_float3(0.f, 1.f - sl, sl), diff, stiff, dampB, dt);
+        wmin.z += ctx.waveShift;
+    }
+
+    if (t != BND_SPHERE) {                                          // System.cu:64-77
+        if (!cylY) {
+            if (noEff || wave) {
+                diff = b - pos.z + wmin.z;
+                if (diff > kBndEps) wall_push(vel, make_float3(0.f, 0.f, 1.f), diff, stiff, dampC, dt);
+            }
+            if (!cycle) {
+                diff = b + pos.z - wmax.z;
+                if (diff > kBndEps) wall_push(vel, make_float3(0.f, 0.f, -1.f), diff, stiff, dampC, dt);
+            }
+        }
+        if (!cylY && !cylZ) {
+            diff = b - pos.x + wmin.x;
+            if (diff > kBndEps) wall_push(vel, make_float3(1.f, 0.f, 0.f), diff, stiff, dampB, dt);
+            diff = b + pos.x - wmax.x;
+            if (diff > kBndEps) wall_push(vel, make_float3(-1.f, 0.f, 0.f), diff, stiff, dampB, dt);
+        }
+        if (!cylZ) {
+            diff = b - pos.y + wmin.y;
+            if (diff > kBndEps) wall_push(vel, make_float3(0.f, 1.f, 0.f), diff, stiff, dampB, dt);
+            diff = b + pos.y - wmax.y;
+            if (diff > kBndEps) wall_push(vel, make_float3(0.f, -1.f, 0.f), diff, stiff, dampB, dt);
+        }
+    } else {                                                        // System.cu:78-81
+        float len = sqrtf(dot3(pos, pos));
+        diff = b + len + wmin.y;
+        if (diff > kBndEps) wall_push(vel, make_float3(-pos.x / len, -pos.y / len, -pos.z / len), diff, stiff, dampC, dt);
+    }
+
+    if (cylY || t == BND_CYL_YZ) {                                  // System.cu:84-86
+        float len = sqrtf(pos.x * pos.x + pos.z * pos.z);
+        diff = b + len - wmax.x;
+        if (diff > kBndEps) wall_push(vel, make_float3(-pos.x / len, 0.f, -pos.z / len), diff, stiff, dampC, dt);
+    }
+    if (cylZ || t == BND_CYL_YZ) {                                  // System.cu:89-91
+        float len = sqrtf(pos.x * pos.x + pos.y * pos.y);
+        diff = b + len + wmin.y;
+        if (diff > kBndEps) wall_push(vel, make_float3(-pos.x / len, -pos.y / len, 0.f), diff, stiff, dampC, dt);
+    }
+
+    if (!wave && !noEff) {                                          // wrap / cycle in Z, System.cu:94-97
+        float dr = 1.f * par.particleR;
+        if (cycle && vel.z > par.rVexit && pos.z > wmax.z - b - dr)  pos.z -= wmax.z - wmin.z - 2 * b - dr;
+        else if (vel.z < -par.rVexit && pos.z < wmin.z + b + dr)     pos.z += wmax.z - wmin.z - 2 * b - dr;
+    }
+
+    if (t == BND_PUMP_Y) {                                          // System.cu:101-158
+        const float rad = wmax.x, ang = par.angOut, hc = par.hClose, rin = rad * par.radIn;
+        float len = sqrtf(pos.x * pos.x + pos.y * pos.y);
+        diff = b + len - rad;
+        if (diff > kBndEps) {                                       // cylinder frame
+            float a = atanf(pos.x / pos.y);
+            bool hit = ang < 0.5f ? (a < -ang || a > ang || pos.y < 0)
+                                  : (pos.y < 0 || (len < rad * par.s5 && a < ang));
+            if (hit) wall_push(vel, make_float3(-pos.x / len, -pos.y / len, 0.f), diff, stiff, dampB, dt);
+        }
+        float xs;                                                   // outlet box
+        if (ang < 0.5f) {
+            xs = sinf(ang * par.s3) * rad;
+            float zs = cosf(ang * par.s3) * rad * par.s4;
+            if (pos.y > zs) {
+                diff = b - pos.x - xs;
+                if (diff > kBndEps) wall_push(vel, make_float3(1.f, 0.f, 0.f), diff, stiff, dampB, dt);
+                diff = b + pos.x - xs;
+                if (diff > kBndEps) wall_push(vel, make_float3(-1.f, 0.f, 0.f), diff, stiff, dampB, dt);
+            }
+        } else {
+            xs = 0.09f * par.s4;
+            if (len >= rad * par.s6) {
+                diff = b - pos.x + xs;
+                if (diff > kBndEps) wall_push(vel, make_float3(1.f, 0.f, 0.f), diff, stiff, dampB, dt);
+            }
+        }
+        if (pos.z > hc - b * par.s1) {                              // inlet hole
+            diff = b + len - rin;
+            if (diff > kBndEps) wall_push(vel, make_float3(-pos.x / len, -pos.y / len, 0.f), diff, stiff, dampB, dt);
+        }
+        if (pos.z < hc - b * par.s2) {
+            diff = b + pos.z - hc;
+            if (diff > kBndEps) wall_push(vel, make_float3(0.f, 0.f, -1.f), diff, stiff, dampB, dt);
+        }
+        diff = pos.y - wmax.y + par.rDexit;                         // exit -> inlet teleport
+        if (diff > kBndEps && vel.y > par.rVexit) {
+            float aa, rr;
+            float zz = fabsf(hc - wmin.z);
+            if (ang < 0.5f) {
+                float xx = xs * 2;
+                rr = (pos.x + xx / 2) / xx * 0.7f;
+                aa = (pos.z - zz / 2) / zz * 1.6f;
+            } else {
+                rr = (wmax.x - pos.x) / xs * 0.45f;
+                aa = (pos.z - zz / 2) / zz * 1.8f;
+            }
+            rr *= rin;  aa *= 2.f * PI;
+            float x = cosf(aa) * rr, y = sinf(aa) * rr;
+            // the reference multiplies by the double literal 0.01 here (System.cu:154)
+            float z = (float)((double)(wmax.z - b) - (double)fabsf(vel.y - par.rVexit) * 0.01);
+            pos = make_float3(x, y, z);
+            vel = make_float3(vel.x, vel.z, -vel.y);
+        }
+    }
+}
+
+// calcGridPos + calcGridHash: true division per component, floor, z-major linear hash.
+__device__ __forceinline__ uint32_t cell_hash(const SimParams& par, float3 p)
+{
+    int gx = (int)floorf((p.x - par.worldMin.x) / par.cellSize.x);
+    int gy = (int)floorf((p.y - par.worldMin.y) / par.cellSize.y);
+    int gz = (int)floorf((p.z - par.worldMin.z) / par.cellSize.z);
+    return (uint32_t)(gz * (int)par.gridSize_yx + gy * (int)par.gridSize.x + gx);
+}
+
+__global__ void __launch_bounds__(256)
+k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
+                 float4* __restrict__ pos, float4* __restrict__ vel,
+                 uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU,
+                 uint32_t* __restrict__ cellCount, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p4 = pos[i], v4 = vel[i];
+    float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
+
+    soft_boundary(par, ctx, p, v);
+
+    const float dt = par.timeStep;                                  // System.cu:177-179
+    v.x += par.gravity.x * dt;  v.y += par.gravity.y * dt;  v.z += par.gravity.z * dt;
+    v.x *= par.globalDamping;   v.y *= par.globalDamping;   v.z *= par.globalDamping;
+    p.x += v.x * dt;            p.y += v.y * dt;            p.z += v.z * dt;
+
+    const float hb = par.distBndHard;                               // System.cu:193-200
+    if (p.x > par.worldMax.x - hb) p.x = par.worldMax.x - hb;
+    if (p.x < par.worldMin.x + hb) p.x = par.worldMin.x + hb;
+    if (p.y > par.worldMax.y - hb) p.y = par.worldMax.y - hb;
+    if (p.y < par.worldMin.y + hb) p.y = par.worldMin.y + hb;
+    if (p.z > par.worldMax.z - hb) p.z = par.worldMax.z - hb;
+    if (p.z < par.worldMin.z + hb) p.z = par.worldMin.z + hb;
+
+    pos[i] = make_float4(p.x, p.y, p.z, p4.w);
+    vel[i] = make_float4(v.x, v.y, v.z, v4.w);
+
+    uint32_t key = cell_hash(par, p);
+    // The hard clamp keeps every finite particle inside the grid.  A NaN position is undefined
+    // behaviour in the reference (out-of-bounds cellStart write); here it lands in the last cell.
+    if (key >= par.numCells) key = par.numCells - 1;
+    keyU[i] = key;
+    rankU[i] = atomicAdd(&cellCount[key], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of the cell histogram: reduce per tile -> scan the tile sums -> scan per tile.
+// The last pass also zeroes the histogram for the next step and records the largest cell.
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+    const int lane = threadIdx.x & 31;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix,
+// total in *total
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* total)
+{
+    __shared__ uint32_t warpSums[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v);
+    if (lane == 31) warpSums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < 8 ? warpSums[lane] : 0u;
+        uint32_t si = warp_incl_scan(s);
+        if (lane < 8) warpSums[lane] = si - s;
+        if (lane == 7) *total = si;
+    }
+    __syncthreads();
+    uint32_t r = incl - v + warpSums[w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_reduce(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tileSums, int numCells)
+{
+    __shared__ uint32_t total;
+    const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
+    uint32_t s = 0;
+    if (base + 16 <= numCells) {
+        const uint4* p = reinterpret_cast<const uint4*>(cnt + base);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) { uint4 q = p[k]; s += q.x + q.y + q.z + q.w; }
+    } else {
+        for (int k = 0; k < 16; k++) if (base + k < numCells) s += cnt[base + k];
+    }
+    block_excl_scan_256(s, &total);
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums in place; tileSums[numTiles] = grand total
+__global__ void __launch_bounds__(256)
+k_scan_tiles(uint32_t* __restrict__ tileSums, int numTiles, uint32_t* __restrict__ maxCount)
+{
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    if (threadIdx.x == 0) *maxCount = 0;
+    for (int base = 0; base < numTiles; base += 256) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < numTiles ? tileSums[i] : 0u;
+        uint32_t ex = block_excl_scan_256(v, &total);
+        if (i < numTiles) tileSums[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tileSums[numTiles] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ tileSums,
+             uint32_t* __restrict__ maxCount, int numCells)
+{
+    __shared__ uint32_t total;
+    const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
+    uint32_t c[16];
+    uint32_t s = 0, mx = 0;
+    const bool full = base + 16 <= numCells;
+    if (full) {
+        uint4* p = reinterpret_cast<uint4*>(cnt + base);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 q = p[k];
+            c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
+            p[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 16; k++) {
+            c[k] = 0;
+            if (base + k < numCells) { c[k] = cnt[base + k]; cnt[base + k] = 0; }
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 16; k++) { s += c[k]; mx = max(mx, c[k]); }
+    uint32_t ex = block_excl_scan_256(s, &total) + tileSums[blockIdx.x];
+    uint32_t o[16];
+    #pragma unroll
+    for (int k = 0; k < 16; k++) { o[k] = ex; ex += c[k]; }
+    if (full) {
+        uint4* p = reinterpret_cast<uint4*>(cellStart + base);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 16; k++) if (base + k < numCells) cellStart[base + k] = o[k];
+    }
+    // cellStart[numCells] = n : the thread that owns the last cell writes it
+    if (base <= numCells - 1 && numCells - 1 < base + 16) cellStart[numCells] = ex;
+
+    // largest cell population (decides whether the neighbour walk must truncate)
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxCount, mx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counting sort, made deterministic and stable.
+//  bucket:       slot j goes to cellStart[key] + (arrival rank from the histogram atomic).  The order
+//                inside a cell is arbitrary at this point.
+//  rank_gather:  every bucketed entry counts how many entries of its cell carry a smaller ORIGINAL
+//                index; that count is its stable rank.  The result is exactly the order a stable
+//                sort by cell hash of the original-order particle list produces, i.e. the
+//                reference's RadixSort output, with no multi-pass radix sort.
+
+__global__ void __launch_bounds__(256)
+k_bucket(const uint32_t* __restrict__ keyU, const uint32_t* __restrict__ rankU, const uint32_t* __restrict__ idxIn,
+         const uint32_t* __restrict__ cellStart, uint2* __restrict__ pairT, int n)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t dst = cellStart[keyU[j]] + rankU[j];
+    pairT[dst] = make_uint2((uint32_t)j, idxIn[j]);
+}
+
+__global__ void __launch_bounds__(256)
+k_rank_gather(const uint2* __restrict__ pairT, const uint32_t* __restrict__ keyU, const uint32_t* __restrict__ cellStart,
+              const float4* __restrict__ posIn, const float4* __restrict__ velIn,
+              float4* __restrict__ posOut, float4* __restrict__ velOut,
+              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, int n)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    uint2 me = pairT[d];
+    uint32_t key = keyU[me.x];
+    uint32_t s = cellStart[key], e = cellStart[key + 1];
+    uint32_t r = 0;
+    for (uint32_t t = s; t < e; t++) r += (pairT[t].y < me.y) ? 1u : 0u;
+    uint32_t f = s + r;
+    float4 p = posIn[me.x], v = velIn[me.x];
+    posOut[f] = p;
+    velOut[f] = v;
+    idxOut[f] = me.y;
+    keyS[f] = key;
+}
+
+__global__ void k_iota(uint32_t* idx, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (uint32_t)i;
+}
+
+__global__ void k_unpermute4(const float4* __restrict__ src, const uint32_t* __restrict__ idx, float4* __restrict__ out,
+                             int start, int count, int n)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t o = idx[j] - (uint32_t)start;
+    if (o < (uint32_t)count) out[o] = src[j];
+}
+
+__global__ void k_unpermute_w(const float4* __restrict__ src, const uint32_t* __restrict__ idx, float* __restrict__ out,
+                              int start, int count, int n)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t o = idx[j] - (uint32_t)start;
+    if (o < (uint32_t)count) out[o] = src[j].w;
+}
+
+__global__ void k_permute4(float4* __restrict__ dst, const uint32_t* __restrict__ idx, const float4* __restrict__ in,
+                           int start, int count, int n)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t o = idx[j] - (uint32_t)start;
+    if (o < (uint32_t)count) dst[j] = in[o];
+}
+
+__global__ void k_cell_table_dump(const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ outStart,
+                                  uint32_t* __restrict__ outEnd, int numCells)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= numCells) return;
+    uint32_t s = cellStart[c], e = cellStart[c + 1];
+    if (outStart) outStart[c] = (s == e) ? 0xffffffffu : s;       // reference cellStart: memset 0xff, set at run starts
+    if (outEnd) outEnd[c] = e;
+}
+
+__global__ void k_pack_pairs(const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ idx, uint2* __restrict__ out, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_uint2(keyS[i], idx[i]);
+}
+
+inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+
+}  // namespace
+
+#define SPH_COUNT(L) do { if ((L).launches) ++*(L).launches; } while (0)
+
+void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel,
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n)
+{
+    BoundaryCtx ctx;
+    ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
+    k_integrate_hash<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, keyU, rankU, cellCount, n);
+    SPH_COUNT(L);
+}
+
+void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* tileSums,
+                     uint32_t* maxCount, int numCells)
+{
+    int tiles = blocks_for(numCells, SPH_SCAN_TILE);
+    k_scan_reduce<<<tiles, 256, 0, L.stream>>>(cellCount, tileSums, numCells);          SPH_COUNT(L);
+    k_scan_tiles<<<1, 256, 0, L.stream>>>(tileSums, tiles, maxCount);                   SPH_COUNT(L);
+    k_scan_apply<<<tiles, 256, 0, L.stream>>>(cellCount, cellStart, tileSums, maxCount, numCells);  SPH_COUNT(L);
+}
+
+void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
+                       const uint32_t* cellStart, uint2* pairT, int n)
+{
+    k_bucket<<<blocks_for(n, 256), 256, 0, L.stream>>>(keyU, rankU, idxIn, cellStart, pairT, n);  SPH_COUNT(L);
+}
+
+void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
+                            const float4* posIn, const float4* velIn,
+                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n)
+{
+    k_rank_gather<<<blocks_for(n, 256), 256, 0, L.stream>>>(pairT, keyU, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, n);
+    SPH_COUNT(L);
+}
+
+void sph_launch_iota(const SphLaunch& L, uint32_t* idx, int n)
+{
+    k_iota<<<blocks_for(n, 256), 256, 0, L.stream>>>(idx, n);  SPH_COUNT(L);
+}
+
+void sph_launch_unpermute4(const SphLaunch& L, const float4* src, const uint32_t* idx, float4* out, int start, int count, int n)
+{
+    k_unpermute4<<<blocks_for(n, 256), 256, 0, L.stream>>>(src, idx, out, start, count, n);  SPH_COUNT(L);
+}
+
+void sph_launch_unpermute_w(const SphLaunch& L, const float4* src, const uint32_t* idx, float* out, int start, int count, int n)
+{
+    k_unpermute_w<<<blocks_for(n, 256), 256, 0, L.stream>>>(src, idx, out, start, count, n);  SPH_COUNT(L);
+}
+
+void sph_launch_permute4(const SphLaunch& L, float4* dst, const uint32_t* idx, const float4* in, int start, int count, int n)
+{
+    k_permute4<<<blocks_for(n, 256), 256, 0, L.stream>>>(dst, idx, in, start, count, n);  SPH_COUNT(L);
+}
+
+void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, uint32_t* outStart, uint32_t* outEnd, int numCells)
+{
+    k_cell_table_dump<<<blocks_for(numCells, 256), 256, 0, L.stream>>>(cellStart, outStart, outEnd, numCells);  SPH_COUNT(L);
+}
+
+void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n)
+{
+    k_pack_pairs<<<blocks_for(n, 256), 256, 0, L.stream>>>(keyS, idx, out, n);  SPH_COUNT(L);
+}

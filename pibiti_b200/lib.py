@@ -1,0 +1,220 @@
+"""ctypes binding of the C ABI in include/sph_b200.h (libsph_b200.so).
+
+There is no fallback of any kind: if the CUDA library is missing or no sm_100 GPU is usable,
+loading / sph_create raise.  SimParams is handled as the 560-byte block it is (numpy structured
+dtype generated from the field table below, which mirrors include/sph_params.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsph_b200.so"
+
+_f3 = ("f4", (3,))
+_u3 = ("u4", (3,))
+_i3 = ("i4", (3,))
+_accel = np.dtype([("pos", *_f3), ("size", *_f3), ("acc", *_f3), ("type", "u4")])
+
+# field order == include/sph_params.h == reference source/CUDA/Params.cuh:53-114
+SIMPARAMS_DTYPE = np.dtype(
+    {
+        "names": [],
+        "formats": [],
+        "offsets": [],
+        "itemsize": 560,
+    }
+)
+
+
+def _build_dtype() -> np.dtype:
+    fields = [
+        ("timeStep", "f4"), ("numParticles", "u4"), ("maxParInCell", "u4"),
+        ("gravity", *_f3), ("globalDamping", "f4"),
+        ("gridSize", *_u3), ("cellSize", *_f3), ("gridSize_yx", "u4"), ("numCells", "u4"),
+        ("worldMin", *_f3), ("worldMax", *_f3), ("worldSize", *_f3),
+        ("worldMinD", *_f3), ("worldMaxD", *_f3), ("worldSizeD", *_f3),
+        ("particleR", "f4"), ("h", "f4"), ("h2", "f4"),
+        ("SpikyKern", "f4"), ("LapKern", "f4"), ("Poly6Kern", "f4"),
+        ("particleMass", "f4"), ("restDensity", "f4"), ("stiffness", "f4"), ("viscosity", "f4"),
+        ("minDens", "f4"), ("minDist", "f4"),
+        ("distBndHard", "f4"), ("distBndSoft", "f4"), ("bndDamp", "f4"), ("bndStiff", "f4"), ("bndDampC", "f4"),
+        ("bndType", "u4"), ("bndEffZ", "u4"),
+        ("collPos", "f4", (4,)), ("collR", "f4"), ("spring", "f4"), ("damping", "f4"), ("shear", "f4"),
+        ("clrType", "u4"), ("iHue", "i4"), ("brightness", "f4"), ("contrast", "f4"),
+        ("dyeType", "i4"), ("dyeClear", "i4"), ("dyeFade", "f4"), ("dyePos", *_f3), ("dyeSize", *_f3),
+        ("acc", _accel, (4,)), ("iHmap", "i4"),
+        ("angOut", "f4"), ("hClose", "f4"), ("radIn", "f4"), ("rVexit", "f4"), ("rDexit", "f4"),
+        ("s1", "f4"), ("s2", "f4"), ("s3", "f4"), ("s4", "f4"), ("s5", "f4"), ("s6", "f4"),
+        ("rAngle", "f4"), ("rTwist", "f4"), ("rotType", "i4"), ("rotBlades", "i4"), ("rotSize", *_i3),
+        ("rotR", "f4"), ("rotSpc", "f4"), ("r2Dist", "f4"), ("r2Angle", "f4"), ("r2twist", "f4"), ("ff2", "f4"),
+    ]
+    # natural packing, except that float4 collPos is 16-byte aligned (offset 208) and the block is
+    # padded to 560 bytes
+    names, formats, offsets = [], [], []
+    off = 0
+    for f in fields:
+        name, fmt = f[0], f[1:]
+        dt = np.dtype(fmt[0] if len(fmt) == 1 else (fmt[0], fmt[1]))
+        if name == "collPos":
+            off = (off + 15) // 16 * 16
+        names.append(name); formats.append(dt); offsets.append(off)
+        off += dt.itemsize
+    assert off <= 560, off
+    return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": 560})
+
+
+SIMPARAMS_DTYPE = _build_dtype()
+assert SIMPARAMS_DTYPE.fields["collPos"][1] == 208 and SIMPARAMS_DTYPE.fields["acc"][1] == 292 \
+    and SIMPARAMS_DTYPE.fields["rAngle"][1] == 500, "SimParams layout drifted from include/sph_params.h"
+
+SPH_POS, SPH_VEL, SPH_DENSITY, SPH_PRESSURE, SPH_COLOR, SPH_DYE = range(6)
+(DUMP_SORTED_PAIRS, DUMP_CELL_START, DUMP_SORTED_POS, DUMP_SORTED_VEL, DUMP_PRESSURE, DUMP_DENSITY,
+ DUMP_NEIGHBOR_COUNTS, DUMP_CELL_END) = range(8)
+STAGE_NAMES = ("integrate_hash", "sort", "reorder", "density", "force")
+
+# every symbol include/sph_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_step", "sph_sync",
+    "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
+    "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
+    "sph_version",
+)
+
+
+class SphError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libsph_b200.so.  Raises if it has not been built -- there is no other code path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SphError(f"{LIB_PATH} is missing: build it with `python -m pibiti_b200.build` "
+                       "(CUDA extension for sm_100a; there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, ci = C.c_void_p, C.c_int
+    lib.sph_create.argtypes = [vp, ci, C.POINTER(vp)]
+    lib.sph_destroy.argtypes = [vp]
+    lib.sph_set_params.argtypes = [vp, vp]
+    lib.sph_get_params.argtypes = [vp, vp]
+    lib.sph_step.argtypes = [vp, ci]
+    lib.sph_sync.argtypes = [vp]
+    lib.sph_set_array.argtypes = [vp, ci, vp, ci, ci]
+    lib.sph_get_array.argtypes = [vp, ci, vp, ci, ci]
+    lib.sph_set_array_device.argtypes = [vp, ci, vp, ci, ci]
+    lib.sph_get_array_device.argtypes = [vp, ci, vp, ci, ci]
+    lib.sph_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.sph_debug_dump.argtypes = [vp, ci, vp, C.c_size_t]
+    lib.sph_get_timings.argtypes = [vp, vp, ci]
+    lib.sph_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.sph_cuda_stream.argtypes = [vp]
+    lib.sph_cuda_stream.restype = vp
+    lib.sph_last_error.argtypes = [vp]
+    lib.sph_last_error.restype = C.c_char_p
+    lib.sph_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def params_array(src=None) -> np.ndarray:
+    """A one-element structured array holding a SimParams block (optionally copied from bytes)."""
+    a = np.zeros(1, SIMPARAMS_DTYPE)
+    if src is not None:
+        a.view(np.uint8)[:] = np.frombuffer(bytes(src), np.uint8, 560)
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SphSystem:
+    """Thin object wrapper over one sph_t handle."""
+
+    def __init__(self, params: np.ndarray, device: int = 0):
+        self.lib = load()
+        self.params = params_array(params.tobytes())
+        self.h = C.c_void_p()
+        rc = self.lib.sph_create(_ptr(self.params), device, C.byref(self.h))
+        if rc != 0:
+            raise SphError(f"sph_create failed ({rc}): {self.lib.sph_last_error(None).decode()}")
+        self.n = int(self.params["numParticles"][0])
+        self.num_cells = int(self.params["numCells"][0])
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise SphError(f"{what} failed ({rc}): {self.lib.sph_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.sph_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params: np.ndarray):
+        self.params = params_array(params.tobytes())
+        self._check(self.lib.sph_set_params(self.h, _ptr(self.params)), "sph_set_params")
+
+    def step(self, nsteps: int = 1):
+        self._check(self.lib.sph_step(self.h, nsteps), "sph_step")
+
+    def sync(self):
+        self._check(self.lib.sph_sync(self.h), "sph_sync")
+
+    def set_array(self, which: int, data: np.ndarray, start: int = 0):
+        data = np.ascontiguousarray(data, np.float32).reshape(-1, 4)
+        self._check(self.lib.sph_set_array(self.h, which, _ptr(data), start, data.shape[0]), "sph_set_array")
+
+    def get_array(self, which: int, start: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n - start if count is None else count
+        shape = (count, 4) if which in (SPH_POS, SPH_VEL, SPH_COLOR) else (count,)
+        out = np.empty(shape, np.float32)
+        self._check(self.lib.sph_get_array(self.h, which, _ptr(out), start, count), "sph_get_array")
+        return out
+
+    def dump(self, what: int) -> np.ndarray:
+        n, c = self.n, self.num_cells
+        spec = {
+            DUMP_SORTED_PAIRS: ((n, 2), np.uint32), DUMP_CELL_START: ((c,), np.uint32), DUMP_CELL_END: ((c,), np.uint32),
+            DUMP_SORTED_POS: ((n, 4), np.float32), DUMP_SORTED_VEL: ((n, 4), np.float32),
+            DUMP_PRESSURE: ((n,), np.float32), DUMP_DENSITY: ((n,), np.float32),
+            DUMP_NEIGHBOR_COUNTS: ((n,), np.uint32),
+        }[what]
+        out = np.empty(spec[0], spec[1])
+        self._check(self.lib.sph_debug_dump(self.h, what, _ptr(out), out.nbytes), "sph_debug_dump")
+        return out
+
+    def enable_timings(self, on: bool = True):
+        self._check(self.lib.sph_get_timings(self.h, None, 1 if on else 0), "sph_get_timings")
+
+    def timings(self) -> dict:
+        ms = np.zeros(5, np.float32)
+        self._check(self.lib.sph_get_timings(self.h, _ptr(ms), 1), "sph_get_timings")
+        return dict(zip(STAGE_NAMES, ms.tolist()))
+
+    def launch_count(self) -> int:
+        v = C.c_longlong(0)
+        self._check(self.lib.sph_kernel_launch_count(self.h, C.byref(v)), "sph_kernel_launch_count")
+        return int(v.value)
+
+    def stream(self) -> int:
+        return int(self.lib.sph_cuda_stream(self.h) or 0)
+
+    def device_buffers(self):
+        p, v, i, cs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.sph_device_buffers(self.h, C.byref(p), C.byref(v), C.byref(i), C.byref(cs)), "sph_device_buffers")
+        return p.value, v.value, i.value, cs.value
