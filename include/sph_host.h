@@ -1,0 +1,136 @@
+// sph_host.h -- the C++ host layer that sits on the C ABI (sph_b200.h): scene parameters,
+// Scenes.xml loading, particle initialisers and the cSPH-shaped system object.
+//
+// It mirrors the interface the reference's App / Graphics layers program against:
+//   class Scene    reference source/SPH/Scene.h:24-62   (Scene.cpp, Scene_Load.cpp)
+//   class Emitter  reference source/SPH/Scene.h:7-19
+//   class cSPH     reference source/SPH/SPH.h:9-50      (SPH_Init/Mem/Update/Util/Scenes.cpp)
+// Same member names and meaning, so code written against `psys->scn.params.*`, `psys->Update()`,
+// `psys->setArray(...)`, `psys->NextScene()` compiles against this header.  What differs, because
+// this layer is headless (no GL, no GLUT):
+//   * positions live in solver-owned device memory, not GL VBOs: getPosBuffer() returns a device
+//     pointer instead of a GL buffer id (posVbo/colorVbo do not exist);
+//   * the App:: statics the reference's SPH layer reaches into (App::emitId, App::dyePos,
+//     App::colliderPos, camera lag, ParamBase::bChangedAny) are members of cSPH::app;
+//   * errors are reported through lastError()/return codes instead of exit(1).
+#ifndef SPH_HOST_H
+#define SPH_HOST_H
+
+#include <string>
+#include <vector>
+#include "sph_params.h"
+#include "sph_b200.h"
+
+static const int NumEmit = 4;       // Scene.h:21
+
+class Emitter {                     // Scene.h:7-19
+public:
+    float3 pos, rot, posLag, rotLag;
+    float vel;
+    int size, size2;
+    Emitter();
+    void IncSize() { if (size < 10) size++; }
+    void DecSize() { if (size > 0) size--; }
+};
+
+namespace sphxml { struct Element; }
+
+class Scene {                       // Scene.h:24-62
+public:
+    char title[40];
+    bool bChapter;
+
+    SimParams params;
+    float fCellSize;
+
+    float3 initMin, initMax;        // init volume
+    int initType, initLast;         // 0 volume / 1 random;  last axis 0 x, 1 y, 2 z
+    float spacing;
+
+    float3 camPos, camRot;
+    float4 collidPos;
+
+    int ce;                         // current emitter
+    Emitter emit[NumEmit];
+    float dropR;
+    int rain;
+
+    int ca;                         // current accelerator
+    float3 accPos[SPH_NUM_ACC];
+
+    float rVel, r2Vel;              // rotor / wave angular velocity
+
+    Scene();                                        // default scene only
+    explicit Scene(const sphxml::Element* s);       // from a <Scene> element
+
+    void InitDefault();
+    void _FromXML(const sphxml::Element* s);
+    void Update();                                  // _UpdatePar + _UpdateGrid
+    void _UpdatePar();
+    void _UpdateGrid();
+};
+
+// program options of the <Options> element (the reference stores them in App:: statics,
+// SPH_Scenes.cpp:99-109)
+struct SphOptions {
+    bool bWindowed = true, bVsyncOff = false, bShowInfo = true;
+    int WSizeX = 0, WSizeY = 0, timAvgCnt = 0;
+    float barsScale = 30.f;
+};
+
+// the App:: state the reference's SPH layer reads and writes
+struct SphAppState {
+    float3 camPosLag, camRotLag, dyePos;    // App.cpp:12 (zero-initialised)
+    float4 colliderPos;                     // App.cpp:13
+    int emitId = 0, cntRain = 0;            // App.cpp:14
+    float inertia = 0.06f;                  // App.cpp:15
+    float fSimTime = 0.f;
+    bool bChangedAny = false;               // ParamBase::bChangedAny (Graphics/param.h:33-34)
+    SphAppState();
+};
+
+class cSPH {                        // SPH.h:9-50
+public:
+    // device >= 0: allocate the solver on that GPU.  device < 0: scene/initialiser layer only
+    // (no GPU touched; Update() fails) -- used to load and inspect Scenes.xml.
+    explicit cSPH(const char* scenesXmlPath = "Scenes.xml", int device = 0);
+    ~cSPH();
+
+    void _InitMem(), _FreeMem();
+    bool bInitialized;
+
+    int Update();                               // one solver step (SPH_Update.cpp:12-81); 0 on success
+    int Update(int nsteps);
+    void Reset(int type);                       // fill the init volume (SPH_Init.cpp:23-79)
+    void Drop(bool bRandom);                    // drop a sphere of particles (SPH_Init.cpp:84-118)
+    void UpdateEmitter();                       // per-step host prologue (App/Update.cpp:9-97)
+    float3 DropPos;
+
+    static SphOptions LoadOptions(const char* scenesXmlPath = "Scenes.xml");
+    void LoadScenes();
+    void InitScene();
+    void NextScene(bool chapter = false);
+    void PrevScene(bool chapter = false);
+    void UpdScene();
+    std::vector<Scene> scenes;
+    Scene scn;
+    int curScene;
+
+    float4* getArray(bool pos);                 // NB inverted flag as in the reference: false = positions, true = velocities
+    void setArray(bool pos, const float4* data, int start, int count);
+    const float4* getPosBuffer() const;         // device pointer (sorted order); reference returns a GL VBO id
+
+    sph_t* solver() const { return sys; }
+    const char* lastError() const { return err.c_str(); }
+
+    float4 *hPos, *hVel;                        // host mirrors, original particle order
+    SphAppState app;
+
+private:
+    std::string xmlPath;
+    int device;
+    sph_t* sys;
+    std::string err;
+};
+
+#endif  // SPH_HOST_H

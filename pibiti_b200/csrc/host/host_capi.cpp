@@ -1,0 +1,112 @@
+// host_capi.cpp -- flat C entry points over the C++ host layer (cSPH / Scene), so that the
+// Python tests and bench.py can drive the same objects the reference's App layer would.
+// Declared in include/sph_host_c.h.
+#include "sph_host.h"
+#include "sph_host_c.h"
+#include "xml_lite.h"
+#include <cstring>
+#include <cstdlib>
+
+extern "C" {
+
+sphh_t* sphh_create(const char* scenesXmlPath, int device)
+{
+    return reinterpret_cast<sphh_t*>(new cSPH(scenesXmlPath, device));
+}
+
+void sphh_destroy(sphh_t* h) { delete reinterpret_cast<cSPH*>(h); }
+
+static cSPH* S(sphh_t* h) { return reinterpret_cast<cSPH*>(h); }
+
+int sphh_num_scenes(sphh_t* h) { return (int)S(h)->scenes.size(); }
+int sphh_cur_scene(sphh_t* h) { return S(h)->curScene; }
+const char* sphh_last_error(sphh_t* h) { return S(h)->lastError(); }
+const char* sphh_scene_title(sphh_t* h, int idx) { return S(h)->scenes[idx].title; }
+
+void sphh_scene_params(sphh_t* h, int idx, struct SimParams* out) { *out = S(h)->scenes[idx].params; }
+
+static void scene_extra(const Scene& s, float* o)
+{
+    int k = 0;
+    o[k++] = s.initMin.x; o[k++] = s.initMin.y; o[k++] = s.initMin.z;
+    o[k++] = s.initMax.x; o[k++] = s.initMax.y; o[k++] = s.initMax.z;
+    o[k++] = (float)s.initType; o[k++] = (float)s.initLast; o[k++] = s.spacing; o[k++] = s.fCellSize;
+    o[k++] = s.dropR; o[k++] = (float)s.rain; o[k++] = s.rVel; o[k++] = s.r2Vel;
+    o[k++] = s.camPos.x; o[k++] = s.camPos.y; o[k++] = s.camPos.z; o[k++] = s.camRot.x; o[k++] = s.camRot.y;
+    o[k++] = s.bChapter ? 1.f : 0.f;
+    for (int e = 0; e < NumEmit; e++) {
+        const Emitter& m = s.emit[e];
+        o[k++] = m.pos.x; o[k++] = m.pos.y; o[k++] = m.pos.z; o[k++] = m.rot.x; o[k++] = m.rot.y;
+        o[k++] = m.vel; o[k++] = (float)m.size; o[k++] = (float)m.size2;
+    }
+    while (k < 64) o[k++] = 0.f;
+}
+void sphh_scene_extra(sphh_t* h, int idx, float* out64) { scene_extra(S(h)->scenes[idx], out64); }
+void sphh_live_extra(sphh_t* h, float* out64) { scene_extra(S(h)->scn, out64); }
+
+void sphh_live_params(sphh_t* h, struct SimParams* out) { *out = S(h)->scn.params; }
+void sphh_set_live_params(sphh_t* h, const struct SimParams* in)
+{
+    S(h)->scn.params = *in;
+    S(h)->app.bChangedAny = true;
+}
+
+int sphh_select_scene(sphh_t* h, int idx)
+{
+    cSPH* s = S(h);
+    if (idx < 0 || idx >= (int)s->scenes.size()) return -1;
+    s->curScene = idx;
+    s->UpdScene();
+    return (int)s->scn.params.numParticles;
+}
+// append a scene built from a <Scene .../> element given as text (synthetic scale-ups go through
+// the same Scene path: every constant is re-derived by Scene::Update); returns its index
+int sphh_add_scene_xml(sphh_t* h, const char* sceneElementXml)
+{
+    cSPH* s = S(h);
+    sphxml::Document doc;
+    if (!doc.Parse(sceneElementXml) || !doc.RootElement()) return -1;
+    Scene sc(doc.RootElement());
+    s->scenes.push_back(sc);
+    return (int)s->scenes.size() - 1;
+}
+void sphh_next_scene(sphh_t* h, int chapter) { S(h)->NextScene(chapter != 0); }
+void sphh_prev_scene(sphh_t* h, int chapter) { S(h)->PrevScene(chapter != 0); }
+
+void sphh_host_arrays(sphh_t* h, float* pos, float* vel)
+{
+    cSPH* s = S(h);
+    size_t n = s->scn.params.numParticles;
+    if (pos) memcpy(pos, s->hPos, n * sizeof(float4));
+    if (vel) memcpy(vel, s->hVel, n * sizeof(float4));
+}
+void sphh_reset(sphh_t* h, int type) { S(h)->Reset(type); }
+int sphh_drop(sphh_t* h, int bRandom) { S(h)->Drop(bRandom != 0);  return S(h)->app.emitId; }
+int sphh_emit_id(sphh_t* h) { return S(h)->app.emitId; }
+void sphh_srand(unsigned seed) { srand(seed); }
+void sphh_update_emitter(sphh_t* h) { S(h)->UpdateEmitter(); }
+int sphh_update(sphh_t* h, int nsteps) { return S(h)->Update(nsteps); }
+void sphh_mark_changed(sphh_t* h) { S(h)->app.bChangedAny = true; }
+
+int sphh_get_array(sphh_t* h, int velocities, float* out)
+{
+    cSPH* s = S(h);
+    float4* p = s->getArray(velocities != 0);
+    if (!p) return -1;
+    memcpy(out, p, (size_t)s->scn.params.numParticles * sizeof(float4));
+    return 0;
+}
+void sphh_set_array(sphh_t* h, int velocities, const float* data, int start, int count)
+{
+    S(h)->setArray(velocities != 0, (const float4*)data, start, count);
+}
+sph_t* sphh_solver(sphh_t* h) { return S(h)->solver(); }
+
+void sphh_load_options(const char* scenesXmlPath, int* out7)
+{
+    SphOptions o = cSPH::LoadOptions(scenesXmlPath);
+    out7[0] = o.bWindowed; out7[1] = o.WSizeX; out7[2] = o.WSizeY; out7[3] = o.bVsyncOff;
+    out7[4] = o.timAvgCnt; out7[5] = (int)o.barsScale; out7[6] = o.bShowInfo;
+}
+
+}  // extern "C"

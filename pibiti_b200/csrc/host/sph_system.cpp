@@ -1,0 +1,433 @@
+// sph_system.cpp -- the cSPH-shaped system object on top of the C ABI.
+//
+// Re-states, headless, what the reference's SPH layer does around the solver:
+//   cSPH::cSPH / Reset / Drop          source/SPH/SPH_Init.cpp:8-118
+//   cSPH::_InitMem / _FreeMem          source/SPH/SPH_Mem.cpp:11-82      (-> sph_create / sph_destroy)
+//   cSPH::Update                       source/SPH/SPH_Update.cpp:12-81   (-> sph_set_params + sph_step)
+//   cSPH::getArray / setArray          source/SPH/SPH_Util.cpp:44-71     (-> sph_get_array / sph_set_array)
+//   InitScene / LoadScenes / Next/Prev source/SPH/SPH_Scenes.cpp:9-111
+//   App::UpdateEmitter                 source/App/Update.cpp:9-97        (per-step host prologue)
+// Random numbers come from the C library's rand(), never seeded, exactly as in the reference
+// (pch/header.h:139-146) so that "random" scenes reproduce.
+#include "sph_host.h"
+#include "xml_lite.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace {
+
+inline float3 f3(float x, float y, float z) { float3 v; v.x = x; v.y = y; v.z = z; return v; }
+inline float4 f4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+
+const float kRandMaxInv = 1.f / float(RAND_MAX);
+inline float frand() { return rand() * kRandMaxInv; }
+inline float random_between(float a, float b) { return (b - a) * float(rand()) * kRandMaxInv + a; }
+inline float len3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }
+
+}  // namespace
+
+cSPH::cSPH(const char* scenesXmlPath, int dev)
+    : bInitialized(false), curScene(0), hPos(nullptr), hVel(nullptr),
+      xmlPath(scenesXmlPath ? scenesXmlPath : "Scenes.xml"), device(dev), sys(nullptr)
+{
+    DropPos = f3(0, 0, 0);
+    LoadScenes();
+}
+
+cSPH::~cSPH() { _FreeMem(); }
+
+// ---- memory ------------------------------------------------------------------------------------
+
+void cSPH::_InitMem()
+{
+    if (bInitialized) return;
+    bInitialized = true;
+    const size_t npar = scn.params.numParticles;
+    hPos = new float4[npar];  memset(hPos, 0, npar * sizeof(float4));
+    hVel = new float4[npar];  memset(hVel, 0, npar * sizeof(float4));
+    if (device >= 0) {
+        int rc = sph_create(&scn.params, device, &sys);
+        if (rc != SPH_OK) { err = sph_last_error(nullptr);  sys = nullptr;  fprintf(stderr, "cSPH: %s\n", err.c_str()); }
+    }
+}
+
+void cSPH::_FreeMem()
+{
+    if (!bInitialized) return;
+    bInitialized = false;
+    delete[] hPos;  hPos = nullptr;
+    delete[] hVel;  hVel = nullptr;
+    if (sys) { sph_destroy(sys);  sys = nullptr; }
+}
+
+// ---- particle initialisers ---------------------------------------------------------------------
+
+void cSPH::Reset(int type)
+{
+    SimParams& p = scn.params;
+    const float r = p.particleR, spc = scn.spacing, b = p.distBndSoft;
+    const float3 cp = f3(p.collPos.x, p.collPos.y, p.collPos.z);
+    float3 wMin = p.worldMinD, wSize = p.worldSizeD;
+    float3 imin = scn.initMin, imax = scn.initMax;
+    const float4 vel0 = f4(0, 0, 0, 0);
+    imin.y += r;
+    wMin.x += r;  wMin.y += r;  wMin.z += r;
+    wSize.x -= 2 * r;  wSize.y -= 2 * r;  wSize.z -= 2 * r;
+    const uint n = p.numParticles;
+    uint i = 0;
+
+    if (type == 1) {                    // uniform random in the (inset) world box
+        for (i = 0; i < n; ++i) {
+            hPos[i].x = wMin.x + wSize.x * frand();
+            hPos[i].y = wMin.y + wSize.y * frand();
+            hPos[i].z = wMin.z + wSize.z * frand();
+            hPos[i].w = 1.f;
+            hVel[i] = vel0;
+        }
+    } else {                            // lattice walk through the init volume
+        float4 pos = f4(imin.x, imin.y, imin.z, 1);
+        // advance one lattice step; axis order a (fastest), b, c.  On overflow of the last axis the
+        // walker wraps to its start, as the reference does (SPH_Init.cpp:41-48).
+        auto step3 = [&](float& pa, float amin, float amax, float& pb, float bmin, float bmax, float& pc, float cmin, float cmax) {
+            pa += spc;
+            if (pa >= amax) {
+                pa = amin;  pb += spc;
+                if (pb >= bmax) {
+                    pb = bmin;  pc += spc;
+                    if (pc >= cmax) pc = cmin;
+                }
+            }
+        };
+        auto advance = [&]() {
+            switch (scn.initLast) {
+            default:
+            case 1: step3(pos.x, imin.x, imax.x, pos.z, imin.z, imax.z, pos.y, imin.y, imax.y); break;
+            case 0: step3(pos.y, imin.y, imax.y, pos.z, imin.z, imax.z, pos.x, imin.x, imax.x); break;
+            case 2: step3(pos.x, imin.x, imax.x, pos.y, imin.y, imax.y, pos.z, imin.z, imax.z); break;
+            }
+        };
+        // a lattice that can never satisfy the acceptance test would spin forever in the reference;
+        // give up after visiting far more sites than any volume can hold
+        unsigned long long guard = 0;
+        const unsigned long long guardMax = 4000000000ull;
+
+        if (p.bndType == BND_PUMP_Y) {
+            const float rad = scn.initMax.x, hc = p.hClose - b * 0.90f, rin = rad * p.radIn - b / 2,
+                        xs = sinf(p.angOut * p.s3) * rad - b / 2 - p.particleR;
+            while (i < n && guard++ < guardMax) {
+                bool in =
+                    (p.angOut < 0.5f && pos.y > 0 && pos.z < hc && pos.x < xs && pos.x > -xs) ||
+                    (p.angOut >= 0.5f && pos.y > 0 && pos.z < hc && pos.x > 0.09f * p.s4) ||
+                    sqrtf(pos.x * pos.x + pos.y * pos.y) * 1.01f < (pos.z < hc ? rad : rin);
+                if (in) { hPos[i] = pos;  hVel[i] = vel0;  i++; }
+                advance();
+            }
+        } else {
+            while (i < n && guard++ < guardMax) {
+                bool outsideCollider = len3(pos.x - cp.x, pos.y - cp.y, pos.z - cp.z) > p.collR || p.rotType > 0;
+                if (outsideCollider) {
+                    bool in = p.bndType == BND_BOX || scn.initType >= 9 || p.bndType == BND_CYL_YZ ||
+                              (p.bndType == BND_CYL_Y && sqrtf(pos.x * pos.x + pos.z * pos.z) < imax.x) ||
+                              (p.bndType == BND_CYL_Z && sqrtf(pos.x * pos.x + pos.y * pos.y) < -imin.y) ||
+                              (p.bndType == BND_SPHERE && len3(pos.x, pos.y, pos.z) < -imin.y);
+                    if (in) { hPos[i] = pos;  hVel[i] = vel0;  i++; }
+                }
+                advance();
+            }
+        }
+        if (i < n) {
+            err = "Reset: init volume accepts no lattice site; remaining particles left at zero";
+            fprintf(stderr, "cSPH: %s\n", err.c_str());
+        }
+    }
+    setArray(0, hPos, 0, (int)n);
+    setArray(1, hVel, 0, (int)n);
+}
+
+void cSPH::Drop(bool bRandom)
+{
+    SimParams& p = scn.params;
+    const float r = scn.dropR, spc = scn.spacing, r2 = r * r, db = (r + 1) * spc, d = 0.5f;
+    const float4 vel0 = f4(0, 0, 0, 0);
+    float3 pos = f3(0.5f, 0.5f, 0.5f);
+
+    if (bRandom) {
+        BndType t = p.bndType;
+        pos.y = (t == BND_BOX || t == BND_CYL_Y) ? 1.0f : 0.75f;
+        if (t == BND_BOX || t == BND_CYL_Z) {
+            pos.x = frand();
+            pos.z = frand();
+        } else {
+            float rr = frand(), k = random_between(0, 2 * PI);
+            pos.x = d + d * cosf(k) * rr;
+            pos.z = d - d * sinf(k) * rr;
+        }
+    }
+    const float3 posw = f3(p.worldMinD.x + db + pos.x * (p.worldSizeD.x - db * 2),
+                           p.worldMinD.y + db + pos.y * (p.worldSizeD.y - db * 2),
+                           p.worldMinD.z + db + pos.z * (p.worldSizeD.z - db * 2));
+    DropPos = posw;
+
+    uint size = 0, id = (uint)app.emitId, a = id;
+    const int ir = (int)r;
+    for (int z = -ir; z <= r; z++)
+        for (int y = -ir; y <= r; y++)
+            for (int x = -ir; x <= r; x++)
+                if (x * x + y * y + z * z <= r2 && a < p.numParticles) {
+                    // the reference memcpy()s 16 bytes out of a 12-byte float3 here (SPH_Init.cpp:109),
+                    // leaving w undefined; w = 1 like every other particle
+                    hPos[a] = f4((float)x * spc + posw.x, (float)y * spc + posw.y, (float)z * spc + posw.z, 1.f);
+                    hVel[a] = vel0;
+                    size++;  a++;
+                }
+    setArray(0, &hPos[id], (int)id, (int)size);
+    setArray(1, &hVel[id], (int)id, (int)size);
+
+    const uint num = p.numParticles;
+    app.emitId += (int)size;
+    if ((uint)app.emitId >= num) app.emitId -= (int)num;
+}
+
+// ---- stepping ----------------------------------------------------------------------------------
+
+int cSPH::Update() { return Update(1); }
+
+int cSPH::Update(int nsteps)
+{
+    if (!bInitialized) return SPH_ERR_STATE;
+    if (!sys) { if (err.empty()) err = "cSPH::Update: no solver (constructed without a device)";  return SPH_ERR_STATE; }
+    if (app.bChangedAny) {                                  // SPH_Update.cpp:19-27
+        app.bChangedAny = false;
+        int rc = sph_set_params(sys, &scn.params);
+        if (rc != SPH_OK) { err = sph_last_error(sys);  return rc; }
+    }
+    int rc = sph_step(sys, nsteps);
+    if (rc != SPH_OK) err = sph_last_error(sys);
+    return rc;
+}
+
+// The per-step host prologue the reference runs before cSPH::Update (App::Simulate,
+// source/App/Render.cpp:8-14).  The emitter orientation is the GL matrix Rx(rot.x)*Ry(-rot.y) that
+// the reference builds with glRotatef and reads back (Update.cpp:73-76), written out here.
+void cSPH::UpdateEmitter()
+{
+    Scene& sc = scn;
+    SimParams* p = &sc.params;
+
+    if (sc.rVel != 0.f) {                                   // rotor / wave phase
+        p->rAngle += sc.rVel * p->timeStep;
+        if (p->r2Dist > 0.f) {
+            p->r2Angle += sc.rVel * sc.r2Vel * p->timeStep;
+            p->r2twist = sc.r2Vel < 0.f ? -1.f : 1.f;
+        }
+        app.bChangedAny = true;
+    }
+    if (p->dyeClear > 0) { p->dyeClear--;  app.bChangedAny = true; }
+
+    const float mind = 0.000707f, mind2 = mind * mind;
+    const float inertia = app.inertia;
+    {                                                       // collider follows its target
+        float4 d = f4(app.colliderPos.x - p->collPos.x, app.colliderPos.y - p->collPos.y,
+                      app.colliderPos.z - p->collPos.z, app.colliderPos.w - p->collPos.w);
+        if (fabsf(d.x) > mind || fabsf(d.y) > mind || fabsf(d.z) > mind) {
+            for (int iter = 0; iter < 3; ++iter) {
+                p->collPos.x += d.x * inertia;  p->collPos.y += d.y * inertia;
+                p->collPos.z += d.z * inertia;  p->collPos.w += d.w * inertia;
+                d = f4(app.colliderPos.x - p->collPos.x, app.colliderPos.y - p->collPos.y,
+                       app.colliderPos.z - p->collPos.z, app.colliderPos.w - p->collPos.w);
+            }
+            app.bChangedAny = true;
+        }
+    }
+    {                                                       // current accelerator follows its target
+        Accel& ac = p->acc[sc.ca];
+        float3 ad = f3(sc.accPos[sc.ca].x - ac.pos.x, sc.accPos[sc.ca].y - ac.pos.y, sc.accPos[sc.ca].z - ac.pos.z);
+        if (ad.x * ad.x + ad.y * ad.y + ad.z * ad.z > mind2) {
+            for (int iter = 0; iter < 3; ++iter) {
+                ac.pos.x += ad.x * inertia;  ac.pos.y += ad.y * inertia;  ac.pos.z += ad.z * inertia;
+                ad = f3(sc.accPos[sc.ca].x - ac.pos.x, sc.accPos[sc.ca].y - ac.pos.y, sc.accPos[sc.ca].z - ac.pos.z);
+            }
+            app.bChangedAny = true;
+        }
+    }
+    {                                                       // dye source follows its target
+        float3 dd = f3(app.dyePos.x - p->dyePos.x, app.dyePos.y - p->dyePos.y, app.dyePos.z - p->dyePos.z);
+        if (fabsf(dd.x) > mind || fabsf(dd.y) > mind || fabsf(dd.z) > mind) {
+            for (int iter = 0; iter < 3; ++iter) {
+                p->dyePos.x += dd.x * inertia;  p->dyePos.y += dd.y * inertia;  p->dyePos.z += dd.z * inertia;
+                dd = f3(app.dyePos.x - p->dyePos.x, app.dyePos.y - p->dyePos.y, app.dyePos.z - p->dyePos.z);
+            }
+            app.bChangedAny = true;
+        }
+    }
+
+    for (int e = 0; e < NumEmit; e++) {                     // emitters recycle ring slots
+        Emitter& em = sc.emit[e];
+        if (em.size <= 0) continue;
+        const int eX = em.size, eY = (em.size2 == 0) ? eX : em.size2;
+        const int size = std::min(eX * eY, 100);            // the reference's static buffers hold 100
+        const float spc = sc.spacing;
+        float4 pos[100], vel[100];
+
+        const float ax = em.rotLag.x * (PI / 180.f), ay = -em.rotLag.y * (PI / 180.f);
+        const float ca = cosf(ax), sa = sinf(ax), cb = cosf(ay), sb = sinf(ay);
+        // columns of M = Rx(ax) * Ry(ay); the reference multiplies a vector by the columns
+        const float c0[3] = {cb, sa * sb, -ca * sb}, c1[3] = {0.f, ca, sa}, c2[3] = {sb, -sa * cb, ca * cb};
+        auto mulTr = [&](const float* v, float* rr) {
+            rr[0] = v[0] * c0[0] + v[1] * c0[1] + v[2] * c0[2];
+            rr[1] = v[0] * c1[0] + v[1] * c1[1] + v[2] * c1[2];
+            rr[2] = v[0] * c2[0] + v[1] * c2[1] + v[2] * c2[2];
+        };
+        const float ev[3] = {0.f, 0.f, em.vel};
+        float4 vel4 = f4(0, 0, 0, 0);
+        mulTr(ev, &vel4.x);
+
+        int i = 0;
+        const float z = (eX - 1) * 0.5f, z2 = (eY - 1) * 0.5f;
+        for (int y = 0; y < eY && i < size; y++)
+            for (int x = 0; x < eX && i < size; x++, i++) {
+                const float pp[3] = {(x - z) * spc, (y - z2) * spc, -spc};
+                pos[i] = f4(0, 0, 0, 1.f);
+                mulTr(pp, &pos[i].x);
+                pos[i].x += em.posLag.x;  pos[i].y += em.posLag.y;  pos[i].z += em.posLag.z;
+                vel[i] = vel4;
+            }
+        // a batch never runs past the end of the particle array
+        const int num = (int)sc.params.numParticles;
+        const int cnt = std::min(size, num - app.emitId);
+        setArray(0, pos, app.emitId, cnt);
+        setArray(1, vel, app.emitId, cnt);
+        app.emitId += size;
+        if (app.emitId >= num) app.emitId -= num;
+    }
+
+    if (sc.rain > 0) {                                      // rain
+        app.cntRain++;
+        if (app.cntRain >= sc.rain) { app.cntRain = 0;  Drop(true); }
+    }
+    app.fSimTime += p->timeStep;
+}
+
+// ---- accessors ---------------------------------------------------------------------------------
+
+float4* cSPH::getArray(bool pos)
+{
+    if (!bInitialized) return nullptr;
+    float4* hdata = !pos ? hPos : hVel;                     // SPH_Util.cpp:48-52: false -> positions
+    if (sys) {
+        int rc = sph_get_array(sys, !pos ? SPH_POS : SPH_VEL, (float*)hdata, 0, (int)scn.params.numParticles);
+        if (rc != SPH_OK) err = sph_last_error(sys);
+    }
+    return hdata;
+}
+
+void cSPH::setArray(bool pos, const float4* data, int start, int count)
+{
+    if (!bInitialized || count <= 0) return;
+    if (sys) {
+        int rc = sph_set_array(sys, !pos ? SPH_POS : SPH_VEL, (const float*)data, start, count);
+        if (rc != SPH_OK) err = sph_last_error(sys);
+    }
+    // keep the host mirror coherent when the caller passed its own buffer
+    float4* mirror = !pos ? hPos : hVel;
+    if (data != mirror + start) memcpy(mirror + start, data, (size_t)count * sizeof(float4));
+}
+
+const float4* cSPH::getPosBuffer() const
+{
+    const float* d = nullptr;
+    if (sys) sph_device_buffers(sys, &d, nullptr, nullptr, nullptr);
+    return (const float4*)d;
+}
+
+// ---- scenes ------------------------------------------------------------------------------------
+
+void cSPH::InitScene()
+{
+    _FreeMem();
+    _InitMem();
+    Reset(scn.initType);
+
+    app.camPosLag = scn.camPos;
+    app.camRotLag = scn.camRot;
+    for (int i = 0; i < NumEmit; i++) {
+        scn.emit[i].posLag = scn.emit[i].pos;
+        scn.emit[i].rotLag = scn.emit[i].rot;
+    }
+    for (int i = 0; i < SPH_NUM_ACC; i++) scn.accPos[i] = scn.params.acc[i].pos;
+    app.colliderPos = scn.params.collPos;
+    scn.params.dyePos = app.dyePos;                         // SPH_Scenes.cpp:23
+    app.emitId = 0;
+}
+
+void cSPH::UpdScene()
+{
+    scn = scenes[curScene];
+    InitScene();
+}
+
+void cSPH::NextScene(bool chapter)
+{
+    do { curScene++;  if (curScene >= (int)scenes.size()) curScene = 0; } while (chapter && !scenes[curScene].bChapter);
+    UpdScene();
+}
+
+void cSPH::PrevScene(bool chapter)
+{
+    do { curScene--;  if (curScene < 0) curScene = (int)scenes.size() - 1; } while (chapter && !scenes[curScene].bChapter);
+    UpdScene();
+}
+
+void cSPH::LoadScenes()
+{
+    scenes.clear();
+    sphxml::Document file;
+    file.LoadFile(xmlPath.c_str());
+    const sphxml::Element* root = file.RootElement();
+    const sphxml::Element* s = nullptr;
+    if (!root) {
+        err = "cannot load " + xmlPath + ": " + file.error;
+        fprintf(stderr, "\nError!  Can't load %s (%s)\n", xmlPath.c_str(), file.error.c_str());
+    } else {
+        s = root->FirstChildElement("Scene");
+        if (!s) fprintf(stderr, "Warning:  No <Scene> in xml.\n");
+    }
+
+    int i = -1, ch = 0;
+    curScene = 0;
+    while (s) {
+        if (s->Attribute("default") || s->Attribute("def")) curScene = i + 1;
+        Scene sc(s);
+        scenes.push_back(sc);
+        if (sc.bChapter) ch++;
+        s = s->NextSiblingElement("Scene");
+        i++;
+    }
+    if (i == -1) { Scene sc;  scenes.push_back(sc);  scn = sc; }
+    else scn = scenes[curScene];
+    scenes[0].bChapter = true;
+    InitScene();
+}
+
+SphOptions cSPH::LoadOptions(const char* scenesXmlPath)
+{
+    SphOptions o;
+    sphxml::Document file;
+    file.LoadFile(scenesXmlPath ? scenesXmlPath : "Scenes.xml");
+    const sphxml::Element* root = file.RootElement();
+    const sphxml::Element* opt = root ? root->FirstChildElement("Options") : nullptr;
+    if (!opt) return o;
+    const char* a;
+    auto toInt = [](const char* str) { return (int)strtol(str, nullptr, 0); };
+    if ((a = opt->Attribute("Windowed")))  o.bWindowed = toInt(a) > 0;
+    if ((a = opt->Attribute("WSizeX")))    o.WSizeX = toInt(a);
+    if ((a = opt->Attribute("WSizeY")))    o.WSizeY = toInt(a);
+    if ((a = opt->Attribute("VSyncOff")))  o.bVsyncOff = toInt(a) > 0;
+    if ((a = opt->Attribute("timAvgCnt"))) o.timAvgCnt = toInt(a);
+    if ((a = opt->Attribute("barsScale"))) o.barsScale = (float)toInt(a);
+    if ((a = opt->Attribute("showInfo")))  o.bShowInfo = toInt(a) > 0;
+    return o;
+}
