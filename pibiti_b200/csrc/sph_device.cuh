@@ -12,6 +12,8 @@
 //   keyS     u32[n]     cell hash in sorted order
 //   posP     float4[n]  (x, y, z, pressure) sorted  -- written by density, read by force
 //   velD     float4[n]  (vx, vy, vz, density) sorted -- written by density, read by force
+//   nlist    u16[ceil(n/T)*kMax*T]  neighbour lists (shared-memory slot numbers), CTA-blocked [cta][k][thread]
+//   ncount   u16[n]     list length per particle (0xFFFF: no list)
 //   cellCount u32[C]    histogram, zeroed again by the scan
 //   cellStart u32[C+1]  exclusive scan: cell c owns sorted slots [cellStart[c], cellStart[c+1])
 #pragma once
@@ -45,12 +47,17 @@ void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, u
 void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n);
 
 // ---- sph_pair_kernels.cu ----------------------------------------------------------------------
-struct SphPairConfig { int threads; int cap; };     // CTA size and staged-candidate capacity
-void sph_pair_default_config(SphPairConfig* density, SphPairConfig* force);
-cudaError_t sph_pair_prepare(const SphPairConfig& density, const SphPairConfig& force);
+// One configuration for both kernels: they must tile the particles and stage the candidates
+// identically, because the neighbour lists the density kernel writes hold shared-memory slot numbers.
+struct SphPairConfig { int threads; int cap; int kMax; };   // CTA size, staged-candidate capacity, list length
+void sph_pair_default_config(SphPairConfig* cfg);
+size_t sph_pair_list_entries(const SphPairConfig& cfg, int n);     // uint16 entries of the neighbour-list buffer
+cudaError_t sph_pair_prepare(const SphPairConfig& cfg);
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
-                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts, int n);
+                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
+                        uint16_t* nlist, uint16_t* ncount, int n);
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
-                      const uint32_t* cellStart, const uint32_t* maxCount, float4* velOut, int n);
+                      const uint32_t* cellStart, const uint32_t* maxCount, const uint16_t* nlist, const uint16_t* ncount,
+                      float4* velOut, int n);

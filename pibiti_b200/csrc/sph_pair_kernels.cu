@@ -116,6 +116,15 @@ __device__ __forceinline__ void stage_candidates(StageTable& st, float4* sbuf, i
     __syncthreads();
 }
 
+// ---- neighbour lists -------------------------------------------------------------------------------
+// The density walk already tests every candidate against h; it records the shared-memory slot of
+// each hit so that the force kernel -- which stages the identical candidate layout -- evaluates only
+// real neighbours (about 25 of 82 candidates) with no divergence on the range test.
+// Layout: CTA-blocked, [cta][k][thread] uint16, so hit k of 32 consecutive particles is one 64-byte
+// segment.  ncount[i] = number of hits, or kListInvalid when the list is unusable (candidate set not
+// staged, or more than kMax hits); such particles take the filtering walk in the force kernel.
+constexpr uint32_t kListInvalid = 0xFFFFu;
+
 // ---- density -------------------------------------------------------------------------------------
 
 // r2 exactly as the CPU evaluates "p.x*p.x + p.y*p.y + p.z*p.z" (no contraction)
@@ -124,41 +133,43 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz)
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void density_span(const float4* __restrict__ cand, uint32_t a, uint32_t e,
-                                             float3 pi, float h2, float& sum, uint32_t& cnt)
+struct ListOut { uint16_t* lst; uint32_t stride; uint32_t kMax; };
+
+template <bool LIST>
+__device__ __forceinline__ void density_span(const float4* __restrict__ cand, int shift, uint32_t a, uint32_t e,
+                                             float3 pi, float h2, float& sum, uint32_t& cnt, const ListOut& lo)
 {
     #pragma unroll 4
     for (uint32_t g = a; g < e; g++) {
-        float4 q = cand[g];
+        float4 q = cand[(int)g + shift];
         float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
         if (r2 < h2) {
             float c = h2 - r2;
             sum += c * c * c;
-            if (COUNT) cnt++;
+            if (LIST) { if (cnt < lo.kMax) lo.lst[cnt * lo.stride] = (uint16_t)((int)g + shift); }
+            cnt++;
         }
     }
 }
 
 // walk [a,e) of the sorted order skipping self; `cand` is indexed by (sorted index + shift)
-template <bool COUNT>
+template <bool LIST>
 __device__ __forceinline__ void density_run(const float4* __restrict__ cand, int shift, uint32_t a, uint32_t e,
-                                            uint32_t self, float3 pi, float h2, float& sum, uint32_t& cnt)
+                                            uint32_t self, float3 pi, float h2, float& sum, uint32_t& cnt, const ListOut& lo)
 {
-    const float4* c = cand + shift;
     if (self - a < e - a) {
-        density_span<COUNT>(c, a, self, pi, h2, sum, cnt);
-        density_span<COUNT>(c, self + 1, e, pi, h2, sum, cnt);
+        density_span<LIST>(cand, shift, a, self, pi, h2, sum, cnt, lo);
+        density_span<LIST>(cand, shift, self + 1, e, pi, h2, sum, cnt, lo);
     } else {
-        density_span<COUNT>(c, a, e, pi, h2, sum, cnt);
+        density_span<LIST>(cand, shift, a, e, pi, h2, sum, cnt, lo);
     }
 }
 
-template <bool STAGED, bool COUNT>
+template <bool STAGED>
 __device__ __forceinline__ void density_particle(const StageTable& st, const float4* __restrict__ sbuf,
                                                  const float4* __restrict__ posS, const uint32_t* __restrict__ cellStart,
                                                  const SimParams& par, bool trunc, uint32_t i, uint32_t key, float3 pi,
-                                                 float& sum, uint32_t& cnt)
+                                                 float& sum, uint32_t& cnt, const ListOut& lo)
 {
     const float h2 = par.h2;
     const long long C = par.numCells;
@@ -173,30 +184,30 @@ __device__ __forceinline__ void density_particle(const StageTable& st, const flo
             cand = sbuf;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
         } else { cand = posS;  shift = 0; }
         if (!trunc) {
-            long long lo = hb - 1, hi = hb + 1;
-            if (lo < 0) lo = 0;
+            long long lo_ = hb - 1, hi = hb + 1;
+            if (lo_ < 0) lo_ = 0;
             if (hi > C - 1) hi = C - 1;
-            if (lo > hi) continue;
-            uint32_t a = __ldg(cellStart + lo), e = __ldg(cellStart + hi + 1);
-            density_run<COUNT>(cand, shift, a, e, i, pi, h2, sum, cnt);
+            if (lo_ > hi) continue;
+            uint32_t a = __ldg(cellStart + lo_), e = __ldg(cellStart + hi + 1);
+            density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lo);
         } else {
             for (int x = -1; x <= 1; x++) {
                 long long h = hb + x;
                 if (h < 0 || h >= C) continue;
                 uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
                 if (e - a > par.maxParInCell) e = a + par.maxParInCell;
-                density_run<COUNT>(cand, shift, a, e, i, pi, h2, sum, cnt);
+                density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lo);
             }
         }
     }
 }
 
-template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_density(const __grid_constant__ SimParams par, int cap,
           const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
           const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
-          float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts, int n)
+          float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
+          uint16_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int kMax, int n)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float4* sbuf = reinterpret_cast<float4*>(smemRaw);
@@ -214,45 +225,70 @@ k_density(const __grid_constant__ SimParams par, int cap,
     const bool trunc = __ldg(maxCount) > par.maxParInCell;
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
 
+    ListOut lo;
+    lo.stride = blockDim.x;  lo.kMax = (uint32_t)kMax;
+    lo.lst = nlist + (size_t)blockIdx.x * kMax * blockDim.x + threadIdx.x;
+
     float sum = 0.f;  uint32_t cnt = 0;
+    bool listOk;
     if (st.staged) {
         if (st.total > 0) mbar_wait(&st.bar, 0);
-        density_particle<true, COUNT>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt);
+        density_particle<true>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lo);
+        listOk = cnt <= (uint32_t)kMax;
     } else {
-        density_particle<false, COUNT>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt);
+        density_particle<false>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lo);
+        listOk = false;
     }
 
     const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
     const float pres = (dens - par.restDensity) * par.stiffness;
     posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
     velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
-    if (COUNT) neighborCounts[i] = cnt;
+    ncount[i] = listOk ? (uint16_t)cnt : (uint16_t)kListInvalid;
+    if (neighborCounts) neighborCounts[i] = cnt;
 }
 
 // ---- force ---------------------------------------------------------------------------------------
 
-struct ForceConsts { float h, minDist, spiky, vterm, minDens; };
+struct ForceConsts { float h, minDist, invMinDist, spiky, vterm, minDens; };
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One pair (reference compForcePair, Kernel_Cell.cui:210-228, with d12 from compForceCell :256).
+// r, 1/r and 1/(rho_i rho_j) use the SFU approximations (rsqrt / rcp, <= 2 ulp): the parity bar for
+// velocities is 1e-5 relative and these stay two orders of magnitude inside it, at a third of the
+// instruction count of IEEE sqrt + two divisions.  Coincident particles (r2 = 0) clamp to minDist as
+// in the reference: fmaxf drops the NaN of 0*inf, fminf the inf of 1/0.
+__device__ __forceinline__ void force_pair(float4 q, float4 u, float3 pi, float3 vi, float presI, float densI,
+                                           const ForceConsts& k, float3& f)
+{
+    float dx = pi.x - q.x, dy = pi.y - q.y, dz = pi.z - q.z;
+    float r2 = dx * dx + dy * dy + dz * dz;
+    float inv = rsqrtf(r2);
+    float r = fmaxf(k.minDist, r2 * inv);
+    float invr = fminf(k.invMinDist, inv);
+    if (r < k.h) {
+        float c = k.h - r;
+        float pterm = c * k.spiky * (presI + q.w) * invr;
+        float d12 = fminf(k.minDens, rcp_approx(densI * u.w));
+        float s = c * d12;
+        f.x += (pterm * dx + k.vterm * (u.x - vi.x)) * s;
+        f.y += (pterm * dy + k.vterm * (u.y - vi.y)) * s;
+        f.z += (pterm * dz + k.vterm * (u.z - vi.z)) * s;
+    }
+}
 
 __device__ __forceinline__ void force_span(const float4* __restrict__ cpp, const float4* __restrict__ cvd,
                                            uint32_t a, uint32_t e, float3 pi, float3 vi, float presI, float densI,
                                            const ForceConsts& k, float3& f)
 {
     #pragma unroll 2
-    for (uint32_t g = a; g < e; g++) {
-        float4 q = cpp[g];
-        float dx = pi.x - q.x, dy = pi.y - q.y, dz = pi.z - q.z;
-        float r = fmaxf(k.minDist, sqrtf(dx * dx + dy * dy + dz * dz));
-        if (r < k.h) {
-            float4 u = cvd[g];
-            float c = k.h - r;
-            float pterm = c * k.spiky * (presI + q.w) / r;
-            float d12 = fminf(k.minDens, 1.0f / (densI * u.w));
-            float s = c * d12;
-            f.x += (pterm * dx + k.vterm * (u.x - vi.x)) * s;
-            f.y += (pterm * dy + k.vterm * (u.y - vi.y)) * s;
-            f.z += (pterm * dz + k.vterm * (u.z - vi.z)) * s;
-        }
-    }
+    for (uint32_t g = a; g < e; g++) force_pair(cpp[g], cvd[g], pi, vi, presI, densI, k, f);
 }
 
 __device__ __forceinline__ void force_run(const float4* __restrict__ cpp, const float4* __restrict__ cvd, int shift,
@@ -269,15 +305,13 @@ __device__ __forceinline__ void force_run(const float4* __restrict__ cpp, const 
     }
 }
 
+// the filtering walk over all candidates (used when a particle has no neighbour list)
 template <bool STAGED>
-__device__ __forceinline__ float3 force_particle(const StageTable& st, const float4* __restrict__ sbuf, int cap,
-                                                 const float4* __restrict__ posP, const float4* __restrict__ velD,
-                                                 const uint32_t* __restrict__ cellStart, const SimParams& par, bool trunc,
-                                                 uint32_t i, uint32_t key, float4 pp, float4 vd)
+__device__ __forceinline__ float3 force_particle_walk(const StageTable& st, const float4* __restrict__ sbuf, int cap,
+                                                      const float4* __restrict__ posP, const float4* __restrict__ velD,
+                                                      const uint32_t* __restrict__ cellStart, const SimParams& par, bool trunc,
+                                                      uint32_t i, uint32_t key, float4 pp, float4 vd, const ForceConsts& k)
 {
-    ForceConsts k;
-    k.h = par.h;  k.minDist = par.minDist;  k.spiky = par.SpikyKern;
-    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
     const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
     const long long C = par.numCells;
     float3 f = make_float3(0.f, 0.f, 0.f);
@@ -333,6 +367,7 @@ __global__ void __launch_bounds__(256)
 k_force(const __grid_constant__ SimParams par, int cap,
         const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
         const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+        const uint16_t* __restrict__ nlist, const uint16_t* __restrict__ ncount, int kMax,
         float4* __restrict__ velOut, int n)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -349,14 +384,32 @@ k_force(const __grid_constant__ SimParams par, int cap,
     const float4 vd = velD[i];
     const float velW = velS[i].w;
     const uint32_t key = keyS[i];
+    const uint32_t cnt = ncount[i];
     const bool trunc = __ldg(maxCount) > par.maxParInCell;
 
-    float3 f;
+    ForceConsts k;
+    k.h = par.h;  k.minDist = par.minDist;  k.invMinDist = 1.0f / par.minDist;  k.spiky = par.SpikyKern;
+    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
+
+    float3 f = make_float3(0.f, 0.f, 0.f);
     if (st.staged) {
         if (st.total > 0) mbar_wait(&st.bar, 0);
-        f = force_particle<true>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd);
+        if (cnt != kListInvalid) {
+            const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+            const uint16_t* lst = nlist + (size_t)blockIdx.x * kMax * blockDim.x + threadIdx.x;
+            const uint32_t stride = blockDim.x;
+            const float4* sPP = sbuf;
+            const float4* sVD = sbuf + cap;
+            #pragma unroll 4
+            for (uint32_t t = 0; t < cnt; t++) {
+                uint32_t slot = lst[t * stride];
+                force_pair(sPP[slot], sVD[slot], pi, vi, pp.w, vd.w, k, f);
+            }
+        } else {
+            f = force_particle_walk<true>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
+        }
     } else {
-        f = force_particle<false>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd);
+        f = force_particle_walk<false>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
     }
 
     const float md = par.particleMass * par.timeStep;                     // System.cu:250
@@ -400,41 +453,42 @@ k_force(const __grid_constant__ SimParams par, int cap,
 
 #define SPH_COUNT(L) do { if ((L).launches) ++*(L).launches; } while (0)
 
-void sph_pair_default_config(SphPairConfig* density, SphPairConfig* force)
+void sph_pair_default_config(SphPairConfig* cfg)
 {
-    density->threads = 128;  density->cap = 1536;
-    force->threads = 128;    force->cap = 1536;
+    cfg->threads = 128;  cfg->cap = 1536;  cfg->kMax = 64;
 }
 
-cudaError_t sph_pair_prepare(const SphPairConfig& d, const SphPairConfig& f)
+size_t sph_pair_list_entries(const SphPairConfig& cfg, int n)
 {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.cap * 16);
+    size_t blocks = ((size_t)n + cfg.threads - 1) / cfg.threads;
+    return blocks * cfg.kMax * cfg.threads;
+}
+
+cudaError_t sph_pair_prepare(const SphPairConfig& cfg)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.cap * 16);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.cap * 16);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, f.cap * 32);
+    return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.cap * 32);
 }
 
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
-                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts, int n)
+                        const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
+                        uint16_t* nlist, uint16_t* ncount, int n)
 {
     int blocks = (n + cfg.threads - 1) / cfg.threads;
-    size_t smem = (size_t)cfg.cap * 16;
-    if (neighborCounts)
-        k_density<true><<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount, posP, velD, neighborCounts, n);
-    else
-        k_density<false><<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount, posP, velD, nullptr, n);
+    k_density<<<blocks, cfg.threads, (size_t)cfg.cap * 16, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount,
+                                                                       posP, velD, neighborCounts, nlist, ncount, cfg.kMax, n);
     SPH_COUNT(L);
 }
 
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
-                      const uint32_t* cellStart, const uint32_t* maxCount, float4* velOut, int n)
+                      const uint32_t* cellStart, const uint32_t* maxCount, const uint16_t* nlist, const uint16_t* ncount,
+                      float4* velOut, int n)
 {
     int blocks = (n + cfg.threads - 1) / cfg.threads;
-    size_t smem = (size_t)cfg.cap * 32;
-    k_force<<<blocks, cfg.threads, smem, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount, velOut, n);
+    k_force<<<blocks, cfg.threads, (size_t)cfg.cap * 32, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
+                                                                     nlist, ncount, cfg.kMax, velOut, n);
     SPH_COUNT(L);
 }

@@ -1,0 +1,300 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: `-m gpu`.
+
+Bars:
+  * bit-exact: cell hashes, sorted (hash, index) pairs, cell table, neighbour counts, and -- because
+    the streaming kernels evaluate floats exactly as the CPU does -- post-integration positions
+    and velocities;
+  * density / pressure / new velocities: relative 1e-5 after one step (REL below), with the floors
+    written next to each check (pressure cancels against rho0*k; velocity components against |v|max).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import sha
+from pibiti_b200 import host, lib
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+TITLES = ["box small default", "Stiff  Dam break", "mini box", "mini dense cells", "mini random", "mini cylinder Y",
+          "mini cylinder Z", "mini sphere", "mini wrap Z", "mini cycle Z", "mini waves", "mini collider accel"]
+
+
+def start(title, oracle, device=0):
+    s = host.CSph(device=device)
+    s.select_scene(title)
+    par = s.params
+    pos, vel = s.host_arrays()
+    o = oracle.system(par)
+    o.set_array(0, pos)
+    o.set_array(1, vel)
+    return s, s.solver(), o, par
+
+
+def check_floats(g, o, par, rel=REL):
+    rho0k = float(par["restDensity"][0]) * float(par["stiffness"][0])
+    dg, do = g.dump(lib.DUMP_DENSITY), o.dump(5)
+    assert np.all(np.abs(dg - do) <= rel * np.abs(do) + 1e-30), "density"
+    pg, po = g.dump(lib.DUMP_PRESSURE), o.dump(4)
+    assert np.all(np.abs(pg - po) <= rel * (np.abs(po) + rho0k)), "pressure"
+    vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+    vmax = max(float(np.abs(vo[:, :3]).max()), 1e-3)
+    assert np.all(np.abs(vg - vo) <= rel * vmax), f"velocity: {np.abs(vg - vo).max()} vs scale {vmax}"
+    return vmax
+
+
+def check_integers_exact(g, o):
+    assert np.array_equal(g.dump(lib.DUMP_SORTED_PAIRS), o.dump(0)), "sorted (hash,index) pairs"
+    cs = g.dump(lib.DUMP_CELL_START)
+    assert np.array_equal(cs, o.dump(1)), "cellStart"
+    assert np.array_equal(g.dump(lib.DUMP_NEIGHBOR_COUNTS), o.dump(6)), "neighbour counts"
+    assert np.array_equal(g.dump(lib.DUMP_SORTED_POS), o.dump(2)), "sortedPos (bit-exact integrate)"
+    assert np.array_equal(g.dump(lib.DUMP_SORTED_VEL), o.dump(3)), "sortedVel (bit-exact integrate)"
+    assert np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0)), "positions, original order"
+
+
+@pytest.mark.parametrize("title", TITLES)
+def test_one_step_parity(oracle_any, golden_steps, title):
+    s, g, o, par = start(title, oracle_any)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    # and against the committed vectors of the reference build
+    key = title.replace(" ", "_")
+    assert sha(g.dump(lib.DUMP_SORTED_PAIRS)) == str(golden_steps[f"{key}/1/pairs_sha"])
+    assert sha(g.dump(lib.DUMP_NEIGHBOR_COUNTS)) == str(golden_steps[f"{key}/1/counts_sha"])
+    assert sha(g.dump(lib.DUMP_CELL_START)) == str(golden_steps[f"{key}/1/cellStart_sha"])
+    assert sha(g.get_array(lib.SPH_POS)) == str(golden_steps[f"{key}/1/pos_sha"])
+    gd = golden_steps[f"{key}/1/density_sample"]
+    assert np.all(np.abs(g.dump(lib.DUMP_DENSITY)[::64] - gd) <= REL * np.abs(gd) + 1e-30)
+    gv = golden_steps[f"{key}/1/vel_sample"]
+    assert np.all(np.abs(g.get_array(lib.SPH_VEL)[::64] - gv) <= REL * max(float(np.abs(gv).max()), 1e-3))
+    o.close()
+
+
+@pytest.mark.parametrize("title", ["box small default", "Stiff  Dam break", "mini dense cells", "mini waves", "mini wrap Z"])
+def test_trajectory_parity_with_resync(oracle_any, title):
+    """Follow the oracle's trajectory for 12 steps; before every step the GPU state is reset to the
+    oracle's, then both take one step and must meet the one-step bar (integers bit-exact)."""
+    s, g, o, par = start(title, oracle_any)
+    for step in range(12):
+        if "waves" in title:                                    # host prologue advances the wave phase
+            s.UpdateEmitter()
+            par = s.params
+            g.set_params(par)
+            o.set_params(par)
+        g.step(1)
+        o.step(1)
+        check_integers_exact(g, o)
+        check_floats(g, o, par)
+        g.set_array(lib.SPH_POS, o.get_array(0))
+        g.set_array(lib.SPH_VEL, o.get_array(1))
+    o.close()
+
+
+@pytest.mark.parametrize("title", ["box small default", "Stiff  Dam break"])
+def test_free_running_drift_is_bounded(oracle_any, title):
+    """50 steps without resync.  SPH is chaotic, so the bar is statistical: 99 % of the
+    particles within half a lattice spacing, centre of mass / kinetic energy / density mean within 1 %."""
+    s, g, o, par = start(title, oracle_any)
+    spacing = float(s.scene_extra()[8])
+    g.step(50)
+    o.step(50)
+    pg, po = g.get_array(lib.SPH_POS), o.get_array(0)
+    d = np.linalg.norm(pg[:, :3] - po[:, :3], axis=1)
+    assert np.quantile(d, 0.99) <= 0.5 * spacing, np.quantile(d, 0.99)
+    extent = float(np.abs(po[:, :3]).max())
+    assert np.all(np.abs(pg[:, :3].mean(0) - po[:, :3].mean(0)) <= 0.01 * extent)
+    vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+    keg, keo = float((vg[:, :3] ** 2).sum()), float((vo[:, :3] ** 2).sum())
+    assert abs(keg - keo) <= 0.01 * keo
+    assert abs(float(g.dump(lib.DUMP_DENSITY).mean()) - float(o.dump(5).mean())) <= 0.01 * float(o.dump(5).mean())
+    o.close()
+
+
+def test_deterministic_and_order_independent(oracle_any):
+    """The sort uses atomics for bucketing but ranks by original index: two runs give identical bits,
+    and so does a run whose particles were handed over in a shuffled slot order."""
+    s, g, o, par = start("mini dense cells", oracle_any)
+    pos, vel = s.host_arrays()
+    g.step(3)
+    a = [g.dump(k).copy() for k in (lib.DUMP_SORTED_PAIRS, lib.DUMP_DENSITY)] + [g.get_array(lib.SPH_VEL)]
+    g2 = lib.SphSystem(par)
+    g2.set_array(lib.SPH_POS, pos)
+    g2.set_array(lib.SPH_VEL, vel)
+    g2.step(1)                                                  # now slot order != original order
+    g2.set_array(lib.SPH_POS, pos)                              # same particles, written through the permutation
+    g2.set_array(lib.SPH_VEL, vel)
+    g2.step(3)
+    b = [g2.dump(k).copy() for k in (lib.DUMP_SORTED_PAIRS, lib.DUMP_DENSITY)] + [g2.get_array(lib.SPH_VEL)]
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
+    g2.close()
+    o.close()
+
+
+def test_set_get_array_ranges(oracle_any):
+    s, g, o, par = start("mini box", oracle_any)
+    n = g.n
+    rng = np.random.default_rng(5)
+    g.step(2)                                                   # state is in sorted order now
+    o.step(2)
+    g.set_array(lib.SPH_POS, o.get_array(0))                    # full write through the permutation
+    g.set_array(lib.SPH_VEL, o.get_array(1))
+    assert np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0))
+    patch = rng.uniform(-0.05, 0.05, (100, 4)).astype(np.float32)
+    patch[:, 3] = 1
+    g.set_array(lib.SPH_POS, patch, start=1234)
+    o.set_array(0, patch, start=1234)
+    vpatch = rng.uniform(-1, 1, (77, 4)).astype(np.float32)
+    g.set_array(lib.SPH_VEL, vpatch, start=n - 77)
+    o.set_array(1, vpatch, start=n - 77)
+    assert np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0))
+    assert np.array_equal(g.get_array(lib.SPH_VEL), o.get_array(1))
+    assert np.array_equal(g.get_array(lib.SPH_POS, 1200, 200), o.get_array(0, 1200, 200))
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    # density / pressure in original order == oracle's sorted arrays un-permuted
+    idx = o.dump(0)[:, 1]
+    dens = np.empty(n, np.float32)
+    dens[idx] = o.dump(5)
+    assert np.all(np.abs(g.get_array(lib.SPH_DENSITY) - dens) <= REL * dens)
+    with pytest.raises(lib.SphError):
+        g.set_array(lib.SPH_POS, patch, start=n - 5)            # range check
+    o.close()
+
+
+def test_unstaged_fallback_path_matches(oracle_any, monkeypatch):
+    """A staging buffer too small for any CTA forces the global-memory walk; results must not change."""
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", "128,16,16")
+    s, g, o, par = start("mini dense cells", oracle_any)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    o.close()
+
+
+def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch):
+    """Lists shorter than the neighbour count make the force kernel take its filtering walk (staged)."""
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", "128,1536,8")
+    s, g, o, par = start("mini box", oracle_any)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    o.close()
+
+
+@pytest.mark.parametrize("cfg", ["64,1024,64", "256,3072,48"])
+def test_other_cta_shapes_match(oracle_any, monkeypatch, cfg):
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", cfg)
+    s, g, o, par = start("Stiff  Dam break", oracle_any)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    o.close()
+
+
+def test_host_layer_update_and_changed_flag(oracle_any):
+    """cSPH::Update uploads scn.params only when the changed flag is set (SPH_Update.cpp:19-27)."""
+    s, g, o, par = start("mini box", oracle_any)
+    s.Update()
+    o.step(1)
+    assert np.array_equal(s.getArray(False), o.get_array(0))    # inverted flag: False = positions
+    par2 = par.copy()
+    par2["gravity"] = (0, -3.0, 0)
+    s.set_params(par2)                                          # marks changed
+    o.set_params(par2)
+    s.Update(2)
+    o.step(2)
+    vmax = max(float(np.abs(o.get_array(1)).max()), 1e-3)
+    assert np.all(np.abs(s.getArray(True) - o.get_array(1)) <= 1e-4 * vmax)
+    o.close()
+
+
+def test_one_million_particles_full_compare(oracle_any):
+    """BASELINE config 1b (shipped "Extreme box 1 M") against the oracle, one step, everything."""
+    s, g, o, par = start("Extreme box 1 M", oracle_any)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    check_floats(g, o, par)
+    o.close()
+
+
+def sampled_neighbor_counts(pairs, cell_start, cell_end, spos, par, sample):
+    """Pure-numpy restatement of the neighbour walk for a few particles (small cases only)."""
+    gx, gyx, ncell = int(par["gridSize"][0][0]), int(par["gridSize_yx"][0]), int(par["numCells"][0])
+    mp, h2 = int(par["maxParInCell"][0]), np.float32(par["h2"][0])
+    out = []
+    for i in sample:
+        key = int(pairs[i, 0])
+        cnt = 0
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    h = key + dz * gyx + dy * gx + dx
+                    if h < 0 or h >= ncell:
+                        continue
+                    a, e = int(cell_start[h]), int(cell_end[h])
+                    if a == 0xFFFFFFFF:
+                        continue
+                    e = min(e, a + mp)
+                    for j in range(a, e):
+                        if j == i:
+                            continue
+                        d = spos[i, :3] - spos[j, :3]
+                        r2 = np.float32(np.float32(d[0] * d[0]) + np.float32(d[1] * d[1])) + np.float32(d[2] * d[2])
+                        cnt += bool(np.float32(r2) < h2)
+        out.append(cnt)
+    return np.array(out, np.uint32)
+
+
+def test_eight_million_particles_properties():
+    """BASELINE config 2 at full size, through size-independent properties: the sorted keys ascend, the
+    index array is a permutation, the cell table brackets exactly the runs of equal keys, one Drop lands
+    where cSPH::Drop put it, state stays finite, and sampled neighbour counts match a numpy walk."""
+    s = host.CSph(device=0)
+    s.select_scene("tank 8M drop")
+    s.Drop(False)
+    g = s.solver()
+    par = s.params
+    n = g.n
+    hpos, _ = s.host_arrays()
+    assert np.array_equal(g.get_array(lib.SPH_POS, 0, 4096), hpos[:4096])
+    g.step(3)
+    pairs = g.dump(lib.DUMP_SORTED_PAIRS)
+    keys = pairs[:, 0]
+    assert np.all(keys[1:] >= keys[:-1])
+    seen = np.zeros(n, bool)
+    seen[pairs[:, 1]] = True
+    assert seen.all()
+    same = keys[1:] == keys[:-1]
+    assert np.all(pairs[1:, 1][same] > pairs[:-1, 1][same])     # stable by original index
+    cs, ce = g.dump(lib.DUMP_CELL_START), g.dump(lib.DUMP_CELL_END)
+    occ = np.unique(keys)
+    first = np.searchsorted(keys, occ, "left")
+    last = np.searchsorted(keys, occ, "right")
+    assert np.array_equal(cs[occ], first.astype(np.uint32)) and np.array_equal(ce[occ], last.astype(np.uint32))
+    empty = np.ones(len(cs), bool)
+    empty[occ] = False
+    assert np.all(cs[empty] == 0xFFFFFFFF)
+    spos = g.dump(lib.DUMP_SORTED_POS)
+    dens = g.dump(lib.DUMP_DENSITY)
+    assert np.isfinite(spos).all() and np.isfinite(dens).all() and (dens >= 0).all()
+    wmin, wmax = par["worldMin"][0], par["worldMax"][0]
+    assert np.all(spos[:, :3] >= wmin) and np.all(spos[:, :3] <= wmax)
+    sample = np.random.default_rng(1).integers(0, n, 48)
+    counts = g.dump(lib.DUMP_NEIGHBOR_COUNTS)
+    assert np.array_equal(counts[sample], sampled_neighbor_counts(pairs, cs, ce, spos, par, sample))
+    vel = g.get_array(lib.SPH_VEL)
+    assert np.isfinite(vel).all()
