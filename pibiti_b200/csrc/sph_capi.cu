@@ -20,8 +20,9 @@ struct sph_system {
     float4 *pos[2] = {nullptr, nullptr}, *vel = nullptr, *velS = nullptr, *posP = nullptr, *velD = nullptr, *io = nullptr;
     uint32_t *idx[2] = {nullptr, nullptr}, *keyU = nullptr, *rankU = nullptr, *keyS = nullptr, *counts = nullptr;
     uint2* pairT = nullptr;
-    uint16_t *nlist = nullptr, *ncount = nullptr;
-    uint32_t *cellCount = nullptr, *cellStart = nullptr, *tileSums = nullptr, *maxCount = nullptr;
+    void* nlist = nullptr;
+    uint16_t* ncount = nullptr;
+    uint32_t *cellCount = nullptr, *cellStart = nullptr, *tileSums = nullptr, *maxCount = nullptr, *ctaRows = nullptr;
     int cur = 0;                    // live pos/idx buffer
     bool stepped = false;           // sorted scratch (keyS, posP, velD, cellStart) is valid
     bool wantCounts = false;
@@ -80,7 +81,7 @@ extern "C" int sph_destroy(sph_t* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
-                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount};
+                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -126,9 +127,10 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     } while (0)
 
     sph_pair_default_config(&s->cfg);
-    if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "threads,cap,kMax" -- tuning / test aid
-        int t = 0, c = 0, k = 0;
-        if (sscanf(env, "%d,%d,%d", &t, &c, &k) == 3 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024) {
+    if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1,threads,cap,kMax" -- tuning / test aid
+        char mode[8] = {0};  int t = 0, c = 0, k = 0;
+        if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024) {
+            s->cfg.mode = strcmp(mode, "tma") == 0 ? SPH_PAIR_TMA : SPH_PAIR_L1;
             s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
         }
     }
@@ -136,7 +138,8 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     ALLOC(s->posP, n);    ALLOC(s->velD, n);    ALLOC(s->io, n);
     ALLOC(s->idx[0], n);  ALLOC(s->idx[1], n);  ALLOC(s->keyU, n);  ALLOC(s->rankU, n);  ALLOC(s->keyS, n);
     ALLOC(s->counts, n);  ALLOC(s->pairT, n);
-    ALLOC(s->nlist, sph_pair_list_entries(s->cfg, (int)n));  ALLOC(s->ncount, n);
+    { unsigned char* lb = nullptr;  ALLOC(lb, sph_pair_list_bytes(s->cfg, (int)n));  s->nlist = lb; }  ALLOC(s->ncount, n);
+    ALLOC(s->ctaRows, sph_pair_blocks(s->cfg, (int)n));
     ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
 #undef ALLOC
 
@@ -192,10 +195,10 @@ extern "C" int sph_step(sph_t* s, int nsteps)
                                s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
         if (tm) cudaEventRecord(s->ev[3], s->stream);
         sph_launch_density(L, s->cfg, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
-                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, n);
+                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, n);
         if (tm) cudaEventRecord(s->ev[4], s->stream);
         sph_launch_force(L, s->cfg, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
-                         s->nlist, s->ncount, s->vel, n);
+                         s->nlist, s->ncount, s->ctaRows, s->vel, n);
         if (tm) cudaEventRecord(s->ev[5], s->stream);
         s->cur = outb;
         s->stepped = true;
@@ -323,7 +326,7 @@ extern "C" int sph_debug_dump(sph_t* s, int what, void* out, size_t outBytes)
     case SPH_DUMP_NEIGHBOR_COUNTS:
         // recompute density on the sorted state with counting enabled (same kernel, COUNT=true)
         sph_launch_density(L, s->cfg, s->par, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount,
-                           s->posP, s->velD, s->counts, s->nlist, s->ncount, (int)n);
+                           s->posP, s->velD, s->counts, s->nlist, s->ncount, s->ctaRows, (int)n);
         src = s->counts;  bytes = n * 4;  break;
     default: return fail(s, SPH_ERR_ARG, "sph_debug_dump: unknown item %d", what);
     }

@@ -12,8 +12,9 @@
 //   keyS     u32[n]     cell hash in sorted order
 //   posP     float4[n]  (x, y, z, pressure) sorted  -- written by density, read by force
 //   velD     float4[n]  (vx, vy, vz, density) sorted -- written by density, read by force
-//   nlist    u16[ceil(n/T)*kMax*T]  neighbour lists (shared-memory slot numbers), CTA-blocked [cta][k][thread]
+//   nlist    [ceil(n/T)][kMax][T]  neighbour lists, CTA-blocked: u32 sorted indices (L1 variant) or u16 smem slots (TMA variant)
 //   ncount   u16[n]     list length per particle (0xFFFF: no list)
+//   ctaRows  u32[ceil(n/T)]  rows of each CTA's list block that hold data
 //   cellCount u32[C]    histogram, zeroed again by the scan
 //   cellStart u32[C+1]  exclusive scan: cell c owns sorted slots [cellStart[c], cellStart[c+1])
 #pragma once
@@ -47,17 +48,21 @@ void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, u
 void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n);
 
 // ---- sph_pair_kernels.cu ----------------------------------------------------------------------
-// One configuration for both kernels: they must tile the particles and stage the candidates
-// identically, because the neighbour lists the density kernel writes hold shared-memory slot numbers.
-struct SphPairConfig { int threads; int cap; int kMax; };   // CTA size, staged-candidate capacity, list length
+// Two variants of the density/force pair, same results:
+//   SPH_PAIR_TMA  candidates of a CTA staged in shared memory by TMA bulk copies; neighbour lists hold
+//                 shared-memory slot numbers (uint16).  Both kernels must tile and stage identically.
+//   SPH_PAIR_L1   candidates read through L1 from the sorted arrays; lists hold global sorted indices (uint32).
+enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1 };
+struct SphPairConfig { int mode; int threads; int cap; int kMax; };   // variant, CTA size, staged-candidate capacity, list length
 void sph_pair_default_config(SphPairConfig* cfg);
-size_t sph_pair_list_entries(const SphPairConfig& cfg, int n);     // uint16 entries of the neighbour-list buffer
+size_t sph_pair_blocks(const SphPairConfig& cfg, int n);           // CTAs of the pair kernels
+size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n);       // size of the neighbour-list buffer
 cudaError_t sph_pair_prepare(const SphPairConfig& cfg);
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        uint16_t* nlist, uint16_t* ncount, int n);
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int n);
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
-                      const uint32_t* cellStart, const uint32_t* maxCount, const uint16_t* nlist, const uint16_t* ncount,
-                      float4* velOut, int n);
+                      const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
+                      const uint32_t* ctaRows, float4* velOut, int n);

@@ -1,12 +1,19 @@
 // sph_pair_kernels.cu -- density/pressure and pair-force kernels for sm_100a.
 //
-// One CTA owns a run of consecutive SORTED particles.  Because the cell hash is linear and z-major
+// One CTA owns a run of T consecutive SORTED particles.  Because the cell hash is linear and z-major
 // (reference Kernel_Cell.cui:15-19), the 3x3x3 neighbourhood of that run is nine contiguous ranges
 // of the sorted arrays -- one per (dy,dz) grid row -- so the whole candidate set is staged into
 // shared memory by at most nine 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on
 // one mbarrier; float4 elements keep every source offset 16-byte aligned.  Overlapping ranges are
-// merged first so no candidate is staged twice.  Each thread then walks, for its own particle, the
-// nine 3-cell runs [cellStart[h-1], cellStart[h+2]) out of shared memory.
+// merged first so no candidate is staged twice.
+//
+// density: each thread walks, for its own particle, the nine 3-cell runs [cellStart[h-1],
+//   cellStart[h+2]) out of shared memory, tests every candidate against h, accumulates the Poly6 sum
+//   and appends the shared-memory SLOT of every hit to a per-thread neighbour list held in shared
+//   memory; the CTA's list block then leaves in one TMA bulk store (shared -> global).
+// force:   stages the identical candidate layout (positions+pressure, velocities+density) plus the
+//   CTA's list block with the same mbarrier, and evaluates only the listed neighbours (about 25 of
+//   the 82 candidates), so there is no divergence on the range test and no global load in the loop.
 //
 // Reference semantics kept:
 //   * search radius is always +-1 cell, cells are addressed by unclamped hash arithmetic, and
@@ -24,6 +31,7 @@
 namespace {
 
 constexpr int kRows = 9;
+constexpr uint32_t kListInvalid = 0xFFFFu;     // ncount value: particle has no usable neighbour list
 
 struct StageTable {
     uint32_t g0[kRows], g1[kRows];          // clipped sorted-index range of each (dy,dz) row
@@ -33,6 +41,9 @@ struct StageTable {
     int      nseg;
     uint32_t total;                         // staged candidates
     int      staged;                        // 0: candidate set larger than the staging buffer
+    uint32_t txBytes;                       // bytes the mbarrier waits for (0: nothing in flight)
+    uint32_t listRows;                      // force: rows of the CTA's neighbour-list block
+    unsigned int ctaMax;                    // density: longest valid list of the CTA
     unsigned long long bar;                 // mbarrier
 };
 
@@ -65,15 +76,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dstSmem, const void* srcGloba
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D TMA bulk copy shared -> global; returns when the shared source has been read
+__device__ __forceinline__ void tma_bulk_s2g_and_wait(void* dstGlobal, const void* srcSmem, uint32_t bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dstGlobal), "r"(smem_u32(srcSmem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 
 // Threads 0..8 look up the nine row ranges; thread 0 merges them and issues the bulk copies.
 // Returns after a __syncthreads with st filled in.  NARR arrays of float4 are staged back to back
-// (array a occupies slots [a*cap, a*cap+total)).
+// (array a occupies slots [a*cap, a*cap+total)); `listSrc` (force only) is the CTA's neighbour-list
+// block, copied to `listDst` with the same barrier.
 template <int NARR>
 __device__ __forceinline__ void stage_candidates(StageTable& st, float4* sbuf, int cap, const SimParams& par,
                                                  const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart,
                                                  const float4* __restrict__ arr0, const float4* __restrict__ arr1,
-                                                 int p0, int p1)
+                                                 int p0, int p1,
+                                                 const uint16_t* listSrc, uint16_t* listDst, const uint32_t* __restrict__ ctaRows)
 {
     const int tid = threadIdx.x;
     if (tid < kRows) {
@@ -87,7 +109,8 @@ __device__ __forceinline__ void stage_candidates(StageTable& st, float4* sbuf, i
         if (lo <= hi) { a = __ldg(cellStart + lo); e = __ldg(cellStart + hi + 1); }
         st.g0[tid] = a;  st.g1[tid] = e;
     }
-    if (tid == 0) mbar_init(&st.bar, 1);
+    if (tid == kRows) st.listRows = ctaRows ? __ldg(ctaRows + blockIdx.x) : 0u;
+    if (tid == 0) { mbar_init(&st.bar, 1);  st.ctaMax = 0; }
     __syncthreads();
     if (tid == 0) {
         int nseg = 0;  uint32_t total = 0;
@@ -104,26 +127,45 @@ __device__ __forceinline__ void stage_candidates(StageTable& st, float4* sbuf, i
         for (int s = 0; s < nseg; s++) { st.segS0[s] = total;  total += st.segG1[s] - st.segG0[s]; }
         st.nseg = nseg;  st.total = total;
         st.staged = (total <= (uint32_t)cap) ? 1 : 0;
-        if (st.staged && total > 0) {
-            mbar_expect_tx(&st.bar, total * 16u * NARR);
-            for (int s = 0; s < nseg; s++) {
-                uint32_t len = st.segG1[s] - st.segG0[s];
-                tma_bulk_g2s(sbuf + st.segS0[s], arr0 + st.segG0[s], len * 16u, &st.bar);
-                if (NARR > 1) tma_bulk_g2s(sbuf + cap + st.segS0[s], arr1 + st.segG0[s], len * 16u, &st.bar);
+        uint32_t tx = 0;
+        if (st.staged) {
+            const uint32_t listBytes = listSrc ? st.listRows * blockDim.x * 2u : 0u;
+            tx = total * 16u * NARR + listBytes;
+            if (tx > 0) {
+                mbar_expect_tx(&st.bar, tx);
+                if (listBytes) tma_bulk_g2s(listDst, listSrc, listBytes, &st.bar);
             }
         }
+        st.txBytes = tx;
+    }
+    __syncthreads();
+    // one thread per merged segment issues that segment's bulk copies
+    if (tid < st.nseg && st.staged) {
+        const uint32_t len = st.segG1[tid] - st.segG0[tid];
+        tma_bulk_g2s(sbuf + st.segS0[tid], arr0 + st.segG0[tid], len * 16u, &st.bar);
+        if (NARR > 1) tma_bulk_g2s(sbuf + cap + st.segS0[tid], arr1 + st.segG0[tid], len * 16u, &st.bar);
     }
     __syncthreads();
 }
 
-// ---- neighbour lists -------------------------------------------------------------------------------
-// The density walk already tests every candidate against h; it records the shared-memory slot of
-// each hit so that the force kernel -- which stages the identical candidate layout -- evaluates only
-// real neighbours (about 25 of 82 candidates) with no divergence on the range test.
-// Layout: CTA-blocked, [cta][k][thread] uint16, so hit k of 32 consecutive particles is one 64-byte
-// segment.  ncount[i] = number of hits, or kListInvalid when the list is unusable (candidate set not
-// staged, or more than kMax hits); such particles take the filtering walk in the force kernel.
-constexpr uint32_t kListInvalid = 0xFFFFu;
+// sorted-index bounds [a,e) of the 3-cell run centred on hash hb (clipped to the grid); false if empty
+__device__ __forceinline__ bool run_bounds(const uint32_t* __restrict__ cellStart, long long hb, long long C,
+                                           uint32_t& a, uint32_t& e)
+{
+    long long lo = hb - 1, hi = hb + 1;
+    if (lo < 0) lo = 0;
+    if (hi > C - 1) hi = C - 1;
+    if (lo > hi) { a = e = 0;  return false; }
+    a = __ldg(cellStart + lo);
+    e = __ldg(cellStart + hi + 1);
+    return true;
+}
+
+__device__ __forceinline__ long long row_hash(const SimParams& par, uint32_t key, int r)
+{
+    const int dz = r / 3 - 1, dy = r % 3 - 1;
+    return (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
+}
 
 // ---- density -------------------------------------------------------------------------------------
 
@@ -133,35 +175,41 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz)
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-struct ListOut { uint16_t* lst; uint32_t stride; uint32_t kMax; };
+// Per-thread neighbour list under construction: column `tid` of a [kMax][T] uint16 array in shared
+// memory.  `next` walks down the column; writes stop at `end` but the hit count keeps counting.
+struct ListCursor { uint16_t* next; uint16_t* end; uint32_t strideElems; };
 
+// test candidates [a,e) (sorted indices; smem slot = index + shift)
 template <bool LIST>
 __device__ __forceinline__ void density_span(const float4* __restrict__ cand, int shift, uint32_t a, uint32_t e,
-                                             float3 pi, float h2, float& sum, uint32_t& cnt, const ListOut& lo)
+                                             float3 pi, float h2, float& sum, uint32_t& cnt, ListCursor& lc)
 {
     #pragma unroll 4
     for (uint32_t g = a; g < e; g++) {
-        float4 q = cand[(int)g + shift];
+        const int slot = (int)g + shift;
+        float4 q = cand[slot];
         float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
         if (r2 < h2) {
             float c = h2 - r2;
             sum += c * c * c;
-            if (LIST) { if (cnt < lo.kMax) lo.lst[cnt * lo.stride] = (uint16_t)((int)g + shift); }
             cnt++;
+            if (LIST) {
+                if (lc.next < lc.end) *lc.next = (uint16_t)slot;
+                lc.next += lc.strideElems;
+            }
         }
     }
 }
 
-// walk [a,e) of the sorted order skipping self; `cand` is indexed by (sorted index + shift)
 template <bool LIST>
 __device__ __forceinline__ void density_run(const float4* __restrict__ cand, int shift, uint32_t a, uint32_t e,
-                                            uint32_t self, float3 pi, float h2, float& sum, uint32_t& cnt, const ListOut& lo)
+                                            uint32_t self, float3 pi, float h2, float& sum, uint32_t& cnt, ListCursor& lc)
 {
-    if (self - a < e - a) {
-        density_span<LIST>(cand, shift, a, self, pi, h2, sum, cnt, lo);
-        density_span<LIST>(cand, shift, self + 1, e, pi, h2, sum, cnt, lo);
+    if (self - a < e - a) {                 // a <= self < e: skip self
+        density_span<LIST>(cand, shift, a, self, pi, h2, sum, cnt, lc);
+        density_span<LIST>(cand, shift, self + 1, e, pi, h2, sum, cnt, lc);
     } else {
-        density_span<LIST>(cand, shift, a, e, pi, h2, sum, cnt, lo);
+        density_span<LIST>(cand, shift, a, e, pi, h2, sum, cnt, lc);
     }
 }
 
@@ -169,83 +217,113 @@ template <bool STAGED>
 __device__ __forceinline__ void density_particle(const StageTable& st, const float4* __restrict__ sbuf,
                                                  const float4* __restrict__ posS, const uint32_t* __restrict__ cellStart,
                                                  const SimParams& par, bool trunc, uint32_t i, uint32_t key, float3 pi,
-                                                 float& sum, uint32_t& cnt, const ListOut& lo)
+                                                 float& sum, uint32_t& cnt, ListCursor& lc)
 {
     const float h2 = par.h2;
     const long long C = par.numCells;
-    #pragma unroll 1
-    for (int r = 0; r < kRows; r++) {
-        const int dz = r / 3 - 1, dy = r % 3 - 1;
-        const long long hb = (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
-        const float4* cand;  int shift;
-        if (STAGED) {
-            int sg = st.segOf[r];
-            if (sg < 0) continue;
-            cand = sbuf;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
-        } else { cand = posS;  shift = 0; }
-        if (!trunc) {
-            long long lo_ = hb - 1, hi = hb + 1;
-            if (lo_ < 0) lo_ = 0;
-            if (hi > C - 1) hi = C - 1;
-            if (lo_ > hi) continue;
-            uint32_t a = __ldg(cellStart + lo_), e = __ldg(cellStart + hi + 1);
-            density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lo);
-        } else {
+    if (!trunc) {
+        // bounds of the next row are fetched while the current one is walked
+        uint32_t a, e, an = 0, en = 0;
+        bool ok = run_bounds(cellStart, row_hash(par, key, 0), C, a, e), okn = false;
+        #pragma unroll 1
+        for (int r = 0; r < kRows; r++) {
+            if (r + 1 < kRows) okn = run_bounds(cellStart, row_hash(par, key, r + 1), C, an, en);
+            const float4* cand = posS;  int shift = 0;  bool have = ok;
+            if (STAGED) {
+                int sg = st.segOf[r];
+                have = ok && sg >= 0;
+                cand = sbuf;
+                if (have) shift = (int)st.segS0[sg] - (int)st.segG0[sg];
+            }
+            if (have) {
+                if (r == 4) density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lc);
+                else        density_span<STAGED>(cand, shift, a, e, pi, h2, sum, cnt, lc);
+            }
+            a = an;  e = en;  ok = okn;
+        }
+    } else {
+        #pragma unroll 1
+        for (int r = 0; r < kRows; r++) {
+            const long long hb = row_hash(par, key, r);
+            const float4* cand = posS;  int shift = 0;
+            if (STAGED) {
+                int sg = st.segOf[r];
+                if (sg < 0) continue;
+                cand = sbuf;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
+            }
             for (int x = -1; x <= 1; x++) {
                 long long h = hb + x;
                 if (h < 0 || h >= C) continue;
                 uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
                 if (e - a > par.maxParInCell) e = a + par.maxParInCell;
-                density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lo);
+                density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lc);
             }
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_density(const __grid_constant__ SimParams par, int cap,
+k_density(const __grid_constant__ SimParams par, int cap, int kMax,
           const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
           const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
           float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
-          uint16_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int kMax, int n)
+          uint16_t* __restrict__ nlist, uint16_t* __restrict__ ncount, uint32_t* __restrict__ ctaRows, int n)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float4* sbuf = reinterpret_cast<float4*>(smemRaw);
+    uint16_t* slist = reinterpret_cast<uint16_t*>(smemRaw + (size_t)cap * 16);
     __shared__ StageTable st;
 
-    const int p0 = blockIdx.x * blockDim.x;
-    const int p1 = min(n, p0 + (int)blockDim.x);
-    stage_candidates<1>(st, sbuf, cap, par, keyS, cellStart, posS, nullptr, p0, p1);
-
+    const int T = blockDim.x;
+    const int p0 = blockIdx.x * T;
+    const int p1 = min(n, p0 + T);
     const int i = p0 + threadIdx.x;
-    if (i >= p1) return;
-    const float4 p4 = posS[i];
-    const float4 v4 = velS[i];
-    const uint32_t key = keyS[i];
+    const bool active = i < p1;
+    const int il = min(i, p1 - 1);
+    const float4 p4 = posS[il];                 // issued before the staging prologue: latency overlaps it
+    const float4 v4 = velS[il];
+    const uint32_t key = keyS[il];
     const bool trunc = __ldg(maxCount) > par.maxParInCell;
-    const float3 pi = make_float3(p4.x, p4.y, p4.z);
 
-    ListOut lo;
-    lo.stride = blockDim.x;  lo.kMax = (uint32_t)kMax;
-    lo.lst = nlist + (size_t)blockIdx.x * kMax * blockDim.x + threadIdx.x;
+    stage_candidates<1>(st, sbuf, cap, par, keyS, cellStart, posS, nullptr, p0, p1, nullptr, nullptr, nullptr);
 
-    float sum = 0.f;  uint32_t cnt = 0;
-    bool listOk;
-    if (st.staged) {
-        if (st.total > 0) mbar_wait(&st.bar, 0);
-        density_particle<true>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lo);
-        listOk = cnt <= (uint32_t)kMax;
-    } else {
-        density_particle<false>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lo);
-        listOk = false;
+    uint32_t validLen = 0;
+    if (active) {
+        const float3 pi = make_float3(p4.x, p4.y, p4.z);
+
+        ListCursor lc;
+        lc.next = slist + threadIdx.x;
+        lc.end = slist + (size_t)kMax * T;
+        lc.strideElems = (uint32_t)T;
+
+        float sum = 0.f;  uint32_t cnt = 0;
+        bool listOk = false;
+        if (st.staged) {
+            if (st.txBytes > 0) mbar_wait(&st.bar, 0);
+            density_particle<true>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lc);
+            listOk = cnt <= (uint32_t)kMax;
+        } else {
+            density_particle<false>(st, sbuf, posS, cellStart, par, trunc, (uint32_t)i, key, pi, sum, cnt, lc);
+        }
+
+        const float dens = sum * par.Poly6Kern * par.particleMass;        // Kernel_Cell.cui:194-195
+        const float pres = (dens - par.restDensity) * par.stiffness;
+        posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
+        velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
+        ncount[i] = listOk ? (uint16_t)cnt : (uint16_t)kListInvalid;
+        if (neighborCounts) neighborCounts[i] = cnt;
+        validLen = listOk ? cnt : 0u;
     }
 
-    const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
-    const float pres = (dens - par.restDensity) * par.stiffness;
-    posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
-    velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
-    ncount[i] = listOk ? (uint16_t)cnt : (uint16_t)kListInvalid;
-    if (neighborCounts) neighborCounts[i] = cnt;
+    // the CTA's list block leaves in one bulk store: rows [0, longest valid list)
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, validLen);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(&st.ctaMax, wmax);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t rows = st.staged ? min(st.ctaMax, (unsigned int)kMax) : 0u;
+        ctaRows[blockIdx.x] = rows;
+        if (rows > 0) tma_bulk_s2g_and_wait(nlist + (size_t)blockIdx.x * kMax * T, slist, rows * T * 2u);
+    }
 }
 
 // ---- force ---------------------------------------------------------------------------------------
@@ -317,8 +395,7 @@ __device__ __forceinline__ float3 force_particle_walk(const StageTable& st, cons
     float3 f = make_float3(0.f, 0.f, 0.f);
     #pragma unroll 1
     for (int r = 0; r < kRows; r++) {
-        const int dz = r / 3 - 1, dy = r % 3 - 1;
-        const long long hb = (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
+        const long long hb = row_hash(par, key, r);
         const float4 *c0, *c1;  int shift;
         if (STAGED) {
             int sg = st.segOf[r];
@@ -326,11 +403,8 @@ __device__ __forceinline__ float3 force_particle_walk(const StageTable& st, cons
             c0 = sbuf;  c1 = sbuf + cap;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
         } else { c0 = posP;  c1 = velD;  shift = 0; }
         if (!trunc) {
-            long long lo = hb - 1, hi = hb + 1;
-            if (lo < 0) lo = 0;
-            if (hi > C - 1) hi = C - 1;
-            if (lo > hi) continue;
-            uint32_t a = __ldg(cellStart + lo), e = __ldg(cellStart + hi + 1);
+            uint32_t a, e;
+            if (!run_bounds(cellStart, hb, C, a, e)) continue;
             force_run(c0, c1, shift, a, e, i, pi, vi, pp.w, vd.w, k, f);
         } else {
             for (int x = -1; x <= 1; x++) {
@@ -363,55 +437,9 @@ __device__ __forceinline__ float3 sphere_contact(const SimParams& par, float3 re
     return force;
 }
 
-__global__ void __launch_bounds__(256)
-k_force(const __grid_constant__ SimParams par, int cap,
-        const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
-        const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
-        const uint16_t* __restrict__ nlist, const uint16_t* __restrict__ ncount, int kMax,
-        float4* __restrict__ velOut, int n)
+// F -> dv = F*mass*dt, then sphere collider and accelerators, newVel = vel + dv   (System.cu:247-250,373-402)
+__device__ __forceinline__ float4 finish_velocity(const SimParams& par, float4 pp, float4 vd, float velW, float3 f)
 {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    float4* sbuf = reinterpret_cast<float4*>(smemRaw);
-    __shared__ StageTable st;
-
-    const int p0 = blockIdx.x * blockDim.x;
-    const int p1 = min(n, p0 + (int)blockDim.x);
-    stage_candidates<2>(st, sbuf, cap, par, keyS, cellStart, posP, velD, p0, p1);
-
-    const int i = p0 + threadIdx.x;
-    if (i >= p1) return;
-    const float4 pp = posP[i];
-    const float4 vd = velD[i];
-    const float velW = velS[i].w;
-    const uint32_t key = keyS[i];
-    const uint32_t cnt = ncount[i];
-    const bool trunc = __ldg(maxCount) > par.maxParInCell;
-
-    ForceConsts k;
-    k.h = par.h;  k.minDist = par.minDist;  k.invMinDist = 1.0f / par.minDist;  k.spiky = par.SpikyKern;
-    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
-
-    float3 f = make_float3(0.f, 0.f, 0.f);
-    if (st.staged) {
-        if (st.total > 0) mbar_wait(&st.bar, 0);
-        if (cnt != kListInvalid) {
-            const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
-            const uint16_t* lst = nlist + (size_t)blockIdx.x * kMax * blockDim.x + threadIdx.x;
-            const uint32_t stride = blockDim.x;
-            const float4* sPP = sbuf;
-            const float4* sVD = sbuf + cap;
-            #pragma unroll 4
-            for (uint32_t t = 0; t < cnt; t++) {
-                uint32_t slot = lst[t * stride];
-                force_pair(sPP[slot], sVD[slot], pi, vi, pp.w, vd.w, k, f);
-            }
-        } else {
-            f = force_particle_walk<true>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
-        }
-    } else {
-        f = force_particle_walk<false>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
-    }
-
     const float md = par.particleMass * par.timeStep;                     // System.cu:250
     float3 dv = make_float3(f.x * md, f.y * md, f.z * md);
 
@@ -446,8 +474,178 @@ k_force(const __grid_constant__ SimParams par, int cap,
         }
     }
 
-    velOut[i] = make_float4(vd.x + dv.x, vd.y + dv.y, vd.z + dv.z, velW + 0.0f);   // System.cu:402
+    return make_float4(vd.x + dv.x, vd.y + dv.y, vd.z + dv.z, velW + 0.0f);   // System.cu:402
 }
+
+
+__global__ void __launch_bounds__(256)
+k_force(const __grid_constant__ SimParams par, int cap, int kMax,
+        const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
+        const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+        const uint16_t* __restrict__ nlist, const uint16_t* __restrict__ ncount, const uint32_t* __restrict__ ctaRows,
+        float4* __restrict__ velOut, int n)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    float4* sbuf = reinterpret_cast<float4*>(smemRaw);
+    uint16_t* slist = reinterpret_cast<uint16_t*>(smemRaw + (size_t)cap * 32);
+    __shared__ StageTable st;
+
+    const int T = blockDim.x;
+    const int p0 = blockIdx.x * T;
+    const int p1 = min(n, p0 + T);
+    const int i = p0 + threadIdx.x;
+    const int il = min(i, p1 - 1);              // tail threads load a valid element and discard it
+    // own-particle loads are issued first so that their latency overlaps the staging prologue
+    const float4 pp = posP[il];
+    const float4 vd = velD[il];
+    const float velW = velS[il].w;
+    const uint32_t key = keyS[il];
+    const uint32_t cnt = ncount[il];
+    const bool trunc = __ldg(maxCount) > par.maxParInCell;
+
+    stage_candidates<2>(st, sbuf, cap, par, keyS, cellStart, posP, velD, p0, p1,
+                        nlist + (size_t)blockIdx.x * kMax * T, slist, ctaRows);
+    if (i >= p1) return;
+
+    ForceConsts k;
+    k.h = par.h;  k.minDist = par.minDist;  k.invMinDist = 1.0f / par.minDist;  k.spiky = par.SpikyKern;
+    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
+
+    float3 f = make_float3(0.f, 0.f, 0.f);
+    if (st.staged) {
+        if (st.txBytes > 0) mbar_wait(&st.bar, 0);
+        if (cnt != kListInvalid) {
+            const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+            const uint16_t* lst = slist + threadIdx.x;
+            const float4* sPP = sbuf;
+            const float4* sVD = sbuf + cap;
+            #pragma unroll 4
+            for (uint32_t t = 0; t < cnt; t++) {
+                const uint32_t slot = lst[t * T];
+                force_pair(sPP[slot], sVD[slot], pi, vi, pp.w, vd.w, k, f);
+            }
+        } else {
+            f = force_particle_walk<true>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
+        }
+    } else {
+        f = force_particle_walk<false>(st, sbuf, cap, posP, velD, cellStart, par, trunc, (uint32_t)i, key, pp, vd, k);
+    }
+
+    velOut[i] = finish_velocity(par, pp, vd, velW, f);
+}
+
+// ---- L1-cached variant ------------------------------------------------------------------------------
+// Same walk and same arithmetic, but candidates are read straight from the sorted arrays through L1
+// (LDG.128 on the read-only path) instead of being staged by TMA: no shared memory, no CTA prologue,
+// register-limited occupancy.  Neighbour lists hold GLOBAL sorted indices (uint32), CTA-blocked
+// [cta][k][thread] like the staged variant.  Which variant runs is a launch-time choice
+// (SphPairConfig::mode); profiles/ holds the ncu evidence for the default.
+
+__global__ void __launch_bounds__(256)
+k_density_l1(const __grid_constant__ SimParams par, int kMax,
+             const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
+             const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+             float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
+             uint32_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int n)
+{
+    const int T = blockDim.x;
+    const int i = blockIdx.x * T + threadIdx.x;
+    if (i >= n) return;
+    const float4 p4 = posS[i];
+    const float4 v4 = velS[i];
+    const uint32_t key = keyS[i];
+    const bool trunc = __ldg(maxCount) > par.maxParInCell;
+    const float3 pi = make_float3(p4.x, p4.y, p4.z);
+    const float h2 = par.h2;
+    const long long C = par.numCells;
+    uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;
+
+    float sum = 0.f;  uint32_t cnt = 0;
+    auto span = [&](uint32_t a, uint32_t e) {
+        #pragma unroll 4
+        for (uint32_t g = a; g < e; g++) {
+            float4 q = __ldg(posS + g);
+            float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
+            if (r2 < h2) {
+                float c = h2 - r2;
+                sum += c * c * c;
+                if (cnt < (uint32_t)kMax) lst[(size_t)cnt * T] = g;
+                cnt++;
+            }
+        }
+    };
+    auto run = [&](uint32_t a, uint32_t e) {
+        if ((uint32_t)i - a < e - a) { span(a, (uint32_t)i);  span((uint32_t)i + 1, e); }
+        else span(a, e);
+    };
+    if (!trunc) {
+        uint32_t a, e, an = 0, en = 0;
+        bool ok = run_bounds(cellStart, row_hash(par, key, 0), C, a, e), okn = false;
+        #pragma unroll 1
+        for (int r = 0; r < kRows; r++) {
+            if (r + 1 < kRows) okn = run_bounds(cellStart, row_hash(par, key, r + 1), C, an, en);
+            if (ok) { if (r == 4) run(a, e); else span(a, e); }
+            a = an;  e = en;  ok = okn;
+        }
+    } else {
+        #pragma unroll 1
+        for (int r = 0; r < kRows; r++) {
+            const long long hb = row_hash(par, key, r);
+            for (int x = -1; x <= 1; x++) {
+                long long h = hb + x;
+                if (h < 0 || h >= C) continue;
+                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
+                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
+                run(a, e);
+            }
+        }
+    }
+    const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
+    const float pres = (dens - par.restDensity) * par.stiffness;
+    posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
+    velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
+    ncount[i] = cnt <= (uint32_t)kMax ? (uint16_t)cnt : (uint16_t)kListInvalid;
+    if (neighborCounts) neighborCounts[i] = cnt;
+}
+
+__global__ void __launch_bounds__(256)
+k_force_l1(const __grid_constant__ SimParams par, int kMax,
+           const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
+           const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+           const uint32_t* __restrict__ nlist, const uint16_t* __restrict__ ncount,
+           float4* __restrict__ velOut, int n)
+{
+    __shared__ StageTable st;                  // only read by the (never staged) filtering walk
+    const int T = blockDim.x;
+    const int i = blockIdx.x * T + threadIdx.x;
+    if (i >= n) return;
+    const float4 pp = posP[i];
+    const float4 vd = velD[i];
+    const float velW = velS[i].w;
+    const uint32_t cnt = ncount[i];
+
+    ForceConsts k;
+    k.h = par.h;  k.minDist = par.minDist;  k.invMinDist = 1.0f / par.minDist;  k.spiky = par.SpikyKern;
+    k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
+
+    float3 f = make_float3(0.f, 0.f, 0.f);
+    if (cnt != kListInvalid) {
+        const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+        const uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;
+        #pragma unroll 4
+        for (uint32_t t = 0; t < cnt; t++) {
+            const uint32_t g = __ldg(lst + (size_t)t * T);
+            force_pair(__ldg(posP + g), __ldg(velD + g), pi, vi, pp.w, vd.w, k, f);
+        }
+    } else {
+        const bool trunc = __ldg(maxCount) > par.maxParInCell;
+        f = force_particle_walk<false>(st, nullptr, 0, posP, velD, cellStart, par, trunc, (uint32_t)i, keyS[i], pp, vd, k);
+    }
+    velOut[i] = finish_velocity(par, pp, vd, velW, f);
+}
+
+inline size_t density_smem(const SphPairConfig& c) { return (size_t)c.cap * 16 + (size_t)c.kMax * c.threads * 2; }
+inline size_t force_smem(const SphPairConfig& c) { return (size_t)c.cap * 32 + (size_t)c.kMax * c.threads * 2; }
 
 }  // namespace
 
@@ -455,40 +653,50 @@ k_force(const __grid_constant__ SimParams par, int cap,
 
 void sph_pair_default_config(SphPairConfig* cfg)
 {
-    cfg->threads = 128;  cfg->cap = 1536;  cfg->kMax = 64;
+    cfg->mode = SPH_PAIR_L1;  cfg->threads = 128;  cfg->cap = 1344;  cfg->kMax = 48;
 }
 
-size_t sph_pair_list_entries(const SphPairConfig& cfg, int n)
+size_t sph_pair_blocks(const SphPairConfig& cfg, int n) { return ((size_t)n + cfg.threads - 1) / cfg.threads; }
+
+size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n)
 {
-    size_t blocks = ((size_t)n + cfg.threads - 1) / cfg.threads;
-    return blocks * cfg.kMax * cfg.threads;
+    return sph_pair_blocks(cfg, n) * cfg.kMax * cfg.threads * (cfg.mode == SPH_PAIR_TMA ? 2 : 4);
 }
 
 cudaError_t sph_pair_prepare(const SphPairConfig& cfg)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.cap * 16);
+    if (cfg.mode != SPH_PAIR_TMA) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(cfg));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.cap * 32);
+    return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)force_smem(cfg));
 }
 
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        uint16_t* nlist, uint16_t* ncount, int n)
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int n)
 {
-    int blocks = (n + cfg.threads - 1) / cfg.threads;
-    k_density<<<blocks, cfg.threads, (size_t)cfg.cap * 16, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount,
-                                                                       posP, velD, neighborCounts, nlist, ncount, cfg.kMax, n);
+    int blocks = (int)sph_pair_blocks(cfg, n);
+    if (cfg.mode == SPH_PAIR_TMA)
+        k_density<<<blocks, cfg.threads, density_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
+                                                                        posP, velD, neighborCounts, (uint16_t*)nlist, ncount, ctaRows, n);
+    else
+        k_density_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
+                                                           posP, velD, neighborCounts, (uint32_t*)nlist, ncount, n);
     SPH_COUNT(L);
 }
 
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
-                      const uint32_t* cellStart, const uint32_t* maxCount, const uint16_t* nlist, const uint16_t* ncount,
-                      float4* velOut, int n)
+                      const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
+                      const uint32_t* ctaRows, float4* velOut, int n)
 {
-    int blocks = (n + cfg.threads - 1) / cfg.threads;
-    k_force<<<blocks, cfg.threads, (size_t)cfg.cap * 32, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
-                                                                     nlist, ncount, cfg.kMax, velOut, n);
+    int blocks = (int)sph_pair_blocks(cfg, n);
+    if (cfg.mode == SPH_PAIR_TMA)
+        k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
+                                                                    (const uint16_t*)nlist, ncount, ctaRows, velOut, n);
+    else
+        k_force_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
+                                                         (const uint32_t*)nlist, ncount, velOut, n);
     SPH_COUNT(L);
 }

@@ -57,8 +57,15 @@ def check_integers_exact(g, o):
     assert np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0)), "positions, original order"
 
 
+# the two variants of the density/force pair (see pibiti_b200/csrc/sph_device.cuh): "tma,..." stages the
+# candidates in shared memory by TMA bulk copies, "l1,..." reads them through L1.  Format: mode,threads,cap,kMax
+PAIR_VARIANTS = {"l1": "l1,128,1344,48", "tma": "tma,128,1344,48"}
+
+
+@pytest.mark.parametrize("variant", ["l1", "tma"])
 @pytest.mark.parametrize("title", TITLES)
-def test_one_step_parity(oracle_any, golden_steps, title):
+def test_one_step_parity(oracle_any, golden_steps, title, variant, monkeypatch):
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
     s, g, o, par = start(title, oracle_any)
     g.step(1)
     o.step(1)
@@ -77,8 +84,10 @@ def test_one_step_parity(oracle_any, golden_steps, title):
     o.close()
 
 
+@pytest.mark.parametrize("variant", ["l1", "tma"])
 @pytest.mark.parametrize("title", ["box small default", "Stiff  Dam break", "mini dense cells", "mini waves", "mini wrap Z"])
-def test_trajectory_parity_with_resync(oracle_any, title):
+def test_trajectory_parity_with_resync(oracle_any, title, variant, monkeypatch):
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
     """Follow the oracle's trajectory for 12 steps; before every step the GPU state is reset to the
     oracle's, then both take one step and must meet the one-step bar (integers bit-exact)."""
     s, g, o, par = start(title, oracle_any)
@@ -173,7 +182,7 @@ def test_set_get_array_ranges(oracle_any):
 
 def test_unstaged_fallback_path_matches(oracle_any, monkeypatch):
     """A staging buffer too small for any CTA forces the global-memory walk; results must not change."""
-    monkeypatch.setenv("SPH_B200_PAIR_CFG", "128,16,16")
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", "tma,128,16,16")
     s, g, o, par = start("mini dense cells", oracle_any)
     g.step(1)
     o.step(1)
@@ -182,9 +191,10 @@ def test_unstaged_fallback_path_matches(oracle_any, monkeypatch):
     o.close()
 
 
-def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch):
+@pytest.mark.parametrize("variant", ["l1", "tma"])
+def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch, variant):
     """Lists shorter than the neighbour count make the force kernel take its filtering walk (staged)."""
-    monkeypatch.setenv("SPH_B200_PAIR_CFG", "128,1536,8")
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", variant + ",128,1536,8")
     s, g, o, par = start("mini box", oracle_any)
     g.step(1)
     o.step(1)
@@ -193,7 +203,7 @@ def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch):
     o.close()
 
 
-@pytest.mark.parametrize("cfg", ["64,1024,64", "256,3072,48"])
+@pytest.mark.parametrize("cfg", ["tma,64,1024,64", "tma,256,3072,48", "l1,64,16,32", "l1,256,16,64"])
 def test_other_cta_shapes_match(oracle_any, monkeypatch, cfg):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", cfg)
     s, g, o, par = start("Stiff  Dam break", oracle_any)
