@@ -111,6 +111,33 @@ void* sph_cuda_stream(sph_t* s);                                         /* cuda
 const char* sph_last_error(sph_t* s);                                    /* s may be NULL: last create error */
 const char* sph_version(void);
 
+/* ---- slab decomposition: one handle per GPU owns the z-cell layers [zLo, zHi) ------------------------
+ * New in this library (the reference is single-GPU, source/App/App.cpp:142).  The grid is cut into
+ * contiguous z ranges; because the reference only ever looks +-1 cell one ghost layer per
+ * side reproduces its results exactly, and because the cell hash is z-major every layer is a contiguous
+ * run of the sorted arrays.  The handle is created with numParticles = local CAPACITY (owned + ghosts);
+ * all pointers below are DEVICE pointers on the handle's device; the caller moves the buffers between
+ * ranks (pibiti_b200/slab.py does it with torch.distributed send/recv over NCCL).  One step is
+ *   integrate -> take_leavers -> [exchange] -> add_owned -> boundary_particles -> [exchange] -> add_ghosts
+ *   -> sort -> density -> boundary_dp -> [exchange] -> set_ghost_dp -> force
+ * Particle records are SPH_SLAB_RECORD_FLOATS floats: pos xyzw, vel xyzw, (originalIndex as uint32, 0, 0, 0).
+ * Density/pressure records are 8 floats per particle: all (x,y,z,pressure) rows, then all (vx,vy,vz,density) rows.
+ * Functions returning counts synchronise the stream. */
+#define SPH_SLAB_RECORD_FLOATS 12
+int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int hasUpper);
+int sph_slab_set_owned(sph_t* s, const float* d_records, int count);            /* replaces all owned particles */
+int sph_slab_get_owned(sph_t* s, float* d_records, int capacity, int* count);
+int sph_slab_integrate(sph_t* s);
+int sph_slab_take_leavers(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
+int sph_slab_add_owned(sph_t* s, const float* d_records, int count);
+int sph_slab_boundary_particles(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
+int sph_slab_add_ghosts(sph_t* s, const float* d_records, int count);
+int sph_slab_sort(sph_t* s, int* counts3 /* ghosts below, owned, ghosts above */);
+int sph_slab_density(sph_t* s);
+int sph_slab_boundary_dp(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
+int sph_slab_set_ghost_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove);
+int sph_slab_force(sph_t* s);
+
 #ifdef __cplusplus
 }
 #endif

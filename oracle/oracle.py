@@ -68,6 +68,26 @@ class Oracle:
         self.L.orc_sort_pairs(_p(out), out.shape[0])
         return out
 
+    def reorder(self, pairs, old_pos, old_vel, num_cells):
+        n = pairs.shape[0]
+        cell_start = np.empty(num_cells, np.uint32)
+        spos, svel = np.empty((n, 4), np.float32), np.empty((n, 4), np.float32)
+        self.L.orc_reorder(_p(pairs), _p(cell_start), _p(old_pos), _p(old_vel), _p(spos), _p(svel), n, num_cells)
+        return cell_start, spos, svel
+
+    def density(self, spos, pairs, cell_start):
+        n = spos.shape[0]
+        pres, dens = np.empty(n, np.float32), np.empty(n, np.float32)
+        self.L.orc_density(_p(spos), _p(pairs), _p(cell_start), _p(pres), _p(dens), n, cell_start.shape[0])
+        return pres, dens
+
+    def force(self, spos, svel, pres, dens, pairs, cell_start):
+        n = spos.shape[0]
+        new_vel, clr, dye = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
+        self.L.orc_force(_p(spos), _p(svel), _p(pres), _p(dens), _p(pairs), _p(cell_start), _p(new_vel), _p(clr), _p(dye),
+                         n, cell_start.shape[0])
+        return new_vel
+
     def system(self, par: np.ndarray) -> "OracleSystem":
         return OracleSystem(self, par)
 

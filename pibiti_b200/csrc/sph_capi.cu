@@ -30,6 +30,22 @@ struct sph_system {
     SphPairConfig cfg;
     long long launches = 0;
 
+    // slab mode (sph_slab_*): owned z layers [zLo,zHi), one ghost layer towards each existing neighbour
+    struct Slab {
+        bool on = false;
+        int zLo = 0, zHi = 0, hasLower = 0, hasUpper = 0, lowLayers = 0, highLayers = 0;
+        long long keyOffset = 0;
+        int numCellsLocal = 0;
+        int first = 0, count = 0;           // live owned particles: slots [first, first+count) of pos[cur]/vel/idx[cur]
+        int work = 0;                       // end of the work set (owned + appended arrivals + ghosts)
+        int g0 = 0, g1 = 0, g2 = 0;         // after sort: ghosts below [0,g0), owned [g0,g1), ghosts above [g1,g2)
+        int bLoEnd = 0, bHiStart = 0;       // first owned layer [g0,bLoEnd), last owned layer [bHiStart,g1)
+        bool sorted = false;
+        SimParams parLocal;                 // par with numCells = numCellsLocal, for the neighbour walk
+    } slab;
+    uint32_t* counters = nullptr;           // device: 4 append counters
+    uint32_t* hostInts = nullptr;           // pinned: read-back of counters / cell-table entries
+
     bool timing = false;
     cudaEvent_t ev[SPH_STAGE_COUNT + 1] = {};
     float stageMs[SPH_STAGE_COUNT] = {};
@@ -81,8 +97,9 @@ extern "C" int sph_destroy(sph_t* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
-                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows};
+                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters};
     for (void* b : bufs) if (b) cudaFree(b);
+    if (s->hostInts) cudaFreeHost(s->hostInts);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -140,9 +157,11 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     ALLOC(s->counts, n);  ALLOC(s->pairT, n);
     { unsigned char* lb = nullptr;  ALLOC(lb, sph_pair_list_bytes(s->cfg, (int)n));  s->nlist = lb; }  ALLOC(s->ncount, n);
     ALLOC(s->ctaRows, sph_pair_blocks(s->cfg, (int)n));
+    ALLOC(s->counters, 16);
     ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
 #undef ALLOC
 
+    CU_TRY(nullptr, cudaMallocHost((void**)&s->hostInts, 64));
     CU_TRY(nullptr, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& ev : s->ev) CU_TRY(nullptr, cudaEventCreate(&ev));
 
@@ -166,6 +185,10 @@ extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
         return fail(s, SPH_ERR_PARAMS, "sph_set_params: numParticles/numCells exceed the allocation of sph_create");
     if (p->numCells != s->par.numCells || p->numParticles != s->par.numParticles) s->stepped = false;
     s->par = *p;
+    if (s->slab.on) {
+        s->slab.parLocal = *p;
+        s->slab.parLocal.numCells = (uint)s->slab.numCellsLocal;
+    }
     return SPH_OK;
 }
 
@@ -179,6 +202,7 @@ extern "C" int sph_get_params(sph_t* s, struct SimParams* out)
 extern "C" int sph_step(sph_t* s, int nsteps)
 {
     if (!s || nsteps < 0) return SPH_ERR_ARG;
+    if (s->slab.on) return fail(s, SPH_ERR_STATE, "sph_step: handle is in slab mode; drive it with the sph_slab_* phases");
     CU_TRY(s, cudaSetDevice(s->device));
     const int n = (int)s->par.numParticles, C = (int)s->par.numCells;
     SphLaunch L = launcher(s);
@@ -186,19 +210,19 @@ extern "C" int sph_step(sph_t* s, int nsteps)
         const bool tm = s->timing && it == nsteps - 1;
         const int in = s->cur, outb = s->cur ^ 1;
         if (tm) cudaEventRecord(s->ev[0], s->stream);
-        sph_launch_integrate_hash(L, s->par, s->pos[in], s->vel, s->keyU, s->rankU, s->cellCount, n);
+        sph_launch_integrate_hash(L, s->par, s->pos[in], s->vel, s->keyU, s->rankU, s->cellCount, 0, n);
         if (tm) cudaEventRecord(s->ev[1], s->stream);
-        sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, C);
+        sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, C, C);
         sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, n);
         if (tm) cudaEventRecord(s->ev[2], s->stream);
         sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel,
                                s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
         if (tm) cudaEventRecord(s->ev[3], s->stream);
         sph_launch_density(L, s->cfg, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
-                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, n);
+                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, n);
         if (tm) cudaEventRecord(s->ev[4], s->stream);
         sph_launch_force(L, s->cfg, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
-                         s->nlist, s->ncount, s->ctaRows, s->vel, n);
+                         s->nlist, s->ncount, s->ctaRows, s->vel, 0, n);
         if (tm) cudaEventRecord(s->ev[5], s->stream);
         s->cur = outb;
         s->stepped = true;
@@ -326,7 +350,7 @@ extern "C" int sph_debug_dump(sph_t* s, int what, void* out, size_t outBytes)
     case SPH_DUMP_NEIGHBOR_COUNTS:
         // recompute density on the sorted state with counting enabled (same kernel, COUNT=true)
         sph_launch_density(L, s->cfg, s->par, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount,
-                           s->posP, s->velD, s->counts, s->nlist, s->ncount, s->ctaRows, (int)n);
+                           s->posP, s->velD, s->counts, s->nlist, s->ncount, s->ctaRows, 0, (int)n);
         src = s->counts;  bytes = n * 4;  break;
     default: return fail(s, SPH_ERR_ARG, "sph_debug_dump: unknown item %d", what);
     }
@@ -365,3 +389,211 @@ extern "C" int sph_kernel_launch_count(sph_t* s, long long* launches)
 }
 
 extern "C" void* sph_cuda_stream(sph_t* s) { return s ? (void*)s->stream : nullptr; }
+
+// ================================================================================================
+// Slab decomposition
+// ================================================================================================
+
+#define SLAB_CHECK(s)                                                                    \
+    if (!(s)) return SPH_ERR_ARG;                                                        \
+    if (!(s)->slab.on) return fail((s), SPH_ERR_STATE, "handle is not in slab mode (sph_slab_configure)"); \
+    CU_TRY((s), cudaSetDevice((s)->device));
+
+static int slab_read_counters(sph_system* s, int firstCounter, int* out2)
+{
+    CU_TRY(s, cudaMemcpyAsync(s->hostInts, s->counters + firstCounter, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    out2[0] = (int)s->hostInts[0];  out2[1] = (int)s->hostInts[1];
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int hasUpper)
+{
+    if (!s) return SPH_ERR_ARG;
+    const int gz = (int)s->par.gridSize.z;
+    if (zLo < 0 || zHi > gz || zHi - zLo < 1) return fail(s, SPH_ERR_ARG, "sph_slab_configure: bad layer range [%d,%d) of %d", zLo, zHi, gz);
+    if ((hasLower && zLo == 0) || (hasUpper && zHi == gz)) return fail(s, SPH_ERR_ARG, "sph_slab_configure: neighbour beyond the grid");
+    if (s->par.bndEffZ == BND_EFF_WRAP || s->par.bndEffZ == BND_EFF_CYCLE)
+        return fail(s, SPH_ERR_PARAMS, "slab mode does not support the Z wrap/cycle teleport (bndEffZ=1,2): it would make the first and last slab neighbours");
+    sph_system::Slab& b = s->slab;
+    b.on = true;  b.zLo = zLo;  b.zHi = zHi;  b.hasLower = hasLower ? 1 : 0;  b.hasUpper = hasUpper ? 1 : 0;
+    b.lowLayers = b.hasLower;  b.highLayers = b.hasUpper;
+    b.keyOffset = (long long)(zLo - b.lowLayers) * s->par.gridSize_yx;
+    b.numCellsLocal = (int)s->par.gridSize_yx * (zHi - zLo + b.lowLayers + b.highLayers);
+    if (b.numCellsLocal + 1 > s->cellsAlloc) return fail(s, SPH_ERR_PARAMS, "sph_slab_configure: local cell table exceeds the allocation");
+    b.first = b.count = b.work = 0;  b.sorted = false;
+    b.parLocal = s->par;
+    b.parLocal.numCells = (uint)b.numCellsLocal;
+    s->stepped = false;
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_set_owned(sph_t* s, const float* d_records, int count)
+{
+    SLAB_CHECK(s);
+    if (count < 0 || count > s->nAlloc) return fail(s, SPH_ERR_ARG, "sph_slab_set_owned: %d particles exceed capacity %d", count, s->nAlloc);
+    sph_launch_slab_append(launcher(s), d_records, count, s->pos[s->cur], s->vel, s->idx[s->cur], 0);
+    s->slab.first = 0;  s->slab.count = count;  s->slab.work = count;  s->slab.sorted = false;
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_get_owned(sph_t* s, float* d_records, int capacity, int* count)
+{
+    SLAB_CHECK(s);
+    if (!count) return SPH_ERR_ARG;
+    *count = s->slab.count;
+    if (s->slab.count > capacity) return fail(s, SPH_ERR_ARG, "sph_slab_get_owned: buffer holds %d records, need %d", capacity, s->slab.count);
+    sph_launch_slab_export(launcher(s), s->pos[s->cur], s->vel, s->idx[s->cur], s->stepped ? s->posP : nullptr,
+                           s->stepped ? s->velD : nullptr, s->slab.first, s->slab.count, d_records);
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_integrate(sph_t* s)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    SphLaunch L = launcher(s);
+    // everything outside the live owned range is retired (ghosts of the previous step)
+    sph_launch_fill_u32(L, s->idx[s->cur], SPH_DEAD_INDEX, 0, b.first);
+    sph_launch_fill_u32(L, s->idx[s->cur], SPH_DEAD_INDEX, b.first + b.count, b.work - (b.first + b.count));
+    b.work = b.first + b.count;
+    sph_launch_integrate_hash(L, s->par, s->pos[s->cur], s->vel, nullptr, nullptr, nullptr, b.first, b.count);
+    CU_TRY(s, cudaMemsetAsync(s->counters, 0, 4 * sizeof(uint32_t), s->stream));
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_take_leavers(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    sph_launch_slab_take_leavers(launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.first, b.count,
+                                 b.zLo, b.zHi, b.hasLower, b.hasUpper, d_down, capDown, d_up, capUp, s->counters);
+    if (int rc = slab_read_counters(s, 0, counts2)) return rc;
+    if (counts2[0] > capDown || counts2[1] > capUp)
+        return fail(s, SPH_ERR_ARG, "sph_slab_take_leavers: %d/%d leavers exceed the buffers (%d/%d)", counts2[0], counts2[1], capDown, capUp);
+    return SPH_OK;
+}
+
+static int slab_append(sph_system* s, const float* d_records, int count, const char* who)
+{
+    sph_system::Slab& b = s->slab;
+    if (count < 0 || b.work + count > s->nAlloc)
+        return fail(s, SPH_ERR_ARG, "%s: work set %d + %d exceeds capacity %d", who, b.work, count, s->nAlloc);
+    sph_launch_slab_append(launcher(s), d_records, count, s->pos[s->cur], s->vel, s->idx[s->cur], b.work);
+    b.work += count;
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_add_owned(sph_t* s, const float* d_records, int count)
+{
+    SLAB_CHECK(s);
+    return slab_append(s, d_records, count, "sph_slab_add_owned");
+}
+
+extern "C" int sph_slab_boundary_particles(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    sph_launch_slab_boundary(launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.work, b.zLo, b.zHi,
+                             b.hasLower, b.hasUpper, d_down, capDown, d_up, capUp, s->counters);
+    if (int rc = slab_read_counters(s, 2, counts2)) return rc;
+    if (counts2[0] > capDown || counts2[1] > capUp)
+        return fail(s, SPH_ERR_ARG, "sph_slab_boundary_particles: %d/%d exceed the buffers (%d/%d)", counts2[0], counts2[1], capDown, capUp);
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_add_ghosts(sph_t* s, const float* d_records, int count)
+{
+    SLAB_CHECK(s);
+    return slab_append(s, d_records, count, "sph_slab_add_ghosts");
+}
+
+extern "C" int sph_slab_sort(sph_t* s, int* counts3)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    SphLaunch L = launcher(s);
+    const int in = s->cur, outb = s->cur ^ 1, W = b.work, CL = b.numCellsLocal;
+    const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+    sph_launch_slab_hash_hist(L, s->par, s->pos[in], s->idx[in], s->keyU, s->rankU, s->cellCount, W, b.keyOffset, CL);
+    sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL);
+    sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, W);
+    sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W);
+    // five cell-table entries bracket the ghost / owned / boundary-layer ranges
+    const int cells[5] = {b.lowLayers * yx, (b.lowLayers + nz) * yx, CL, (b.lowLayers + 1) * yx, (b.lowLayers + nz - 1) * yx};
+    for (int k = 0; k < 5; k++)
+        CU_TRY(s, cudaMemcpyAsync(s->hostInts + k, s->cellStart + cells[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    b.g0 = (int)s->hostInts[0];  b.g1 = (int)s->hostInts[1];  b.g2 = (int)s->hostInts[2];
+    b.bLoEnd = (int)s->hostInts[3];  b.bHiStart = (int)s->hostInts[4];
+    s->cur = outb;
+    b.first = b.g0;  b.count = b.g1 - b.g0;  b.work = W;  b.sorted = true;
+    if (counts3) { counts3[0] = b.g0;  counts3[1] = b.g1 - b.g0;  counts3[2] = b.g2 - b.g1; }
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_density(sph_t* s)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_density: call sph_slab_sort first");
+    sph_launch_density(launcher(s), s->cfg, b.parLocal, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount,
+                       s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, b.first, b.count);
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_boundary_dp(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_boundary_dp: call sph_slab_sort first");
+    const int nDown = b.hasLower ? b.bLoEnd - b.g0 : 0, nUp = b.hasUpper ? b.g1 - b.bHiStart : 0;
+    if (nDown > capDown || nUp > capUp) return fail(s, SPH_ERR_ARG, "sph_slab_boundary_dp: %d/%d exceed the buffers", nDown, nUp);
+    if (nDown > 0) {
+        CU_TRY(s, cudaMemcpyAsync(d_down, s->posP + b.g0, (size_t)nDown * 16, cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(d_down + 4 * (size_t)nDown, s->velD + b.g0, (size_t)nDown * 16, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    if (nUp > 0) {
+        CU_TRY(s, cudaMemcpyAsync(d_up, s->posP + b.bHiStart, (size_t)nUp * 16, cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(d_up + 4 * (size_t)nUp, s->velD + b.bHiStart, (size_t)nUp * 16, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    counts2[0] = nDown;  counts2[1] = nUp;
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_set_ghost_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    if (nBelow != b.g0 || nAbove != b.g2 - b.g1)
+        return fail(s, SPH_ERR_ARG, "sph_slab_set_ghost_dp: got %d/%d rows for %d/%d ghosts (ghost sets out of step between ranks)",
+                    nBelow, nAbove, b.g0, b.g2 - b.g1);
+    if (nBelow > 0) {
+        CU_TRY(s, cudaMemcpyAsync(s->posP, d_below, (size_t)nBelow * 16, cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(s->velD, d_below + 4 * (size_t)nBelow, (size_t)nBelow * 16, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    if (nAbove > 0) {
+        CU_TRY(s, cudaMemcpyAsync(s->posP + b.g1, d_above, (size_t)nAbove * 16, cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(s->velD + b.g1, d_above + 4 * (size_t)nAbove, (size_t)nAbove * 16, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_force(sph_t* s)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_force: call sph_slab_sort first");
+    sph_launch_force(launcher(s), s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
+                     s->nlist, s->ncount, s->ctaRows, s->vel, b.first, b.count);
+    s->stepped = true;
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}

@@ -31,9 +31,11 @@ struct SphLaunch {
 
 // ---- sph_stream_kernels.cu (compiled with -fmad=false: bit-exact vs the CPU oracle) ----------
 void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel,
-                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n);
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount /*null: integrate only*/,
+                               int first, int count);
+// scan of cells [0,numCells); the largest-cell statistic only looks at cells [0,maxCells)
 void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* blockSums,
-                     uint32_t* maxCount, int numCells);
+                     uint32_t* maxCount, int numCells, int maxCells);
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
                        const uint32_t* cellStart, uint2* pairT, int n);
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
@@ -46,6 +48,22 @@ void sph_launch_unpermute_w(const SphLaunch& L, const float4* src, const uint32_
 void sph_launch_permute4(const SphLaunch& L, float4* dst, const uint32_t* idx, const float4* in, int start, int count, int n);
 void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, uint32_t* outStart, uint32_t* outEnd, int numCells);
 void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n);
+
+// slab mode (records are 48 bytes: float4 pos, float4 vel, uint4 (originalIndex,0,0,0))
+#define SPH_SLAB_RECORD_BYTES 48
+#define SPH_DEAD_INDEX 0xFFFFFFFFu
+void sph_launch_slab_take_leavers(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, uint32_t* idx,
+                                  int first, int count, int zLo, int zHi, int hasLower, int hasUpper,
+                                  void* down, int capDown, void* up, int capUp, uint32_t* counters);
+void sph_launch_slab_boundary(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, const uint32_t* idx,
+                              int n, int zLo, int zHi, int hasLower, int hasUpper,
+                              void* down, int capDown, void* up, int capUp, uint32_t* counters);
+void sph_launch_slab_append(const SphLaunch& L, const void* recs, int count, float4* pos, float4* vel, uint32_t* idx, int at);
+void sph_launch_slab_export(const SphLaunch& L, const float4* pos, const float4* vel, const uint32_t* idx,
+                            const float4* posP, const float4* velD, int first, int count, void* recs);
+void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first, int count);
+void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n, long long keyOffset, int numCellsLocal);
 
 // ---- sph_pair_kernels.cu ----------------------------------------------------------------------
 // Two variants of the density/force pair, same results:
@@ -61,8 +79,8 @@ cudaError_t sph_pair_prepare(const SphPairConfig& cfg);
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int n);
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count);
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
-                      const uint32_t* ctaRows, float4* velOut, int n);
+                      const uint32_t* ctaRows, float4* velOut, int first, int count);

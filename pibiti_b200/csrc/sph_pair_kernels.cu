@@ -267,7 +267,7 @@ k_density(const __grid_constant__ SimParams par, int cap, int kMax,
           const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
           const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
           float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
-          uint16_t* __restrict__ nlist, uint16_t* __restrict__ ncount, uint32_t* __restrict__ ctaRows, int n)
+          uint16_t* __restrict__ nlist, uint16_t* __restrict__ ncount, uint32_t* __restrict__ ctaRows, int first, int n)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float4* sbuf = reinterpret_cast<float4*>(smemRaw);
@@ -275,7 +275,7 @@ k_density(const __grid_constant__ SimParams par, int cap, int kMax,
     __shared__ StageTable st;
 
     const int T = blockDim.x;
-    const int p0 = blockIdx.x * T;
+    const int p0 = first + blockIdx.x * T;     // particles [first, n) are processed
     const int p1 = min(n, p0 + T);
     const int i = p0 + threadIdx.x;
     const bool active = i < p1;
@@ -483,7 +483,7 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
         const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
         const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
         const uint16_t* __restrict__ nlist, const uint16_t* __restrict__ ncount, const uint32_t* __restrict__ ctaRows,
-        float4* __restrict__ velOut, int n)
+        float4* __restrict__ velOut, int first, int n)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float4* sbuf = reinterpret_cast<float4*>(smemRaw);
@@ -491,7 +491,7 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
     __shared__ StageTable st;
 
     const int T = blockDim.x;
-    const int p0 = blockIdx.x * T;
+    const int p0 = first + blockIdx.x * T;     // particles [first, n) are processed
     const int p1 = min(n, p0 + T);
     const int i = p0 + threadIdx.x;
     const int il = min(i, p1 - 1);              // tail threads load a valid element and discard it
@@ -546,10 +546,10 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
              const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
              const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
              float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
-             uint32_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int n)
+             uint32_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int first, int n)
 {
     const int T = blockDim.x;
-    const int i = blockIdx.x * T + threadIdx.x;
+    const int i = first + blockIdx.x * T + threadIdx.x;
     if (i >= n) return;
     const float4 p4 = posS[i];
     const float4 v4 = velS[i];
@@ -613,11 +613,11 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
            const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
            const uint32_t* __restrict__ nlist, const uint16_t* __restrict__ ncount,
-           float4* __restrict__ velOut, int n)
+           float4* __restrict__ velOut, int first, int n)
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
-    const int i = blockIdx.x * T + threadIdx.x;
+    const int i = first + blockIdx.x * T + threadIdx.x;
     if (i >= n) return;
     const float4 pp = posP[i];
     const float4 vd = velD[i];
@@ -674,29 +674,33 @@ cudaError_t sph_pair_prepare(const SphPairConfig& cfg)
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int n)
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count)
 {
-    int blocks = (int)sph_pair_blocks(cfg, n);
+    if (count <= 0) return;
+    const int n = first + count;
+    int blocks = (int)sph_pair_blocks(cfg, count);
     if (cfg.mode == SPH_PAIR_TMA)
         k_density<<<blocks, cfg.threads, density_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
-                                                                        posP, velD, neighborCounts, (uint16_t*)nlist, ncount, ctaRows, n);
+                                                                        posP, velD, neighborCounts, (uint16_t*)nlist, ncount, ctaRows, first, n);
     else
         k_density_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
-                                                           posP, velD, neighborCounts, (uint32_t*)nlist, ncount, n);
+                                                           posP, velD, neighborCounts, (uint32_t*)nlist, ncount, first, n);
     SPH_COUNT(L);
 }
 
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
-                      const uint32_t* ctaRows, float4* velOut, int n)
+                      const uint32_t* ctaRows, float4* velOut, int first, int count)
 {
-    int blocks = (int)sph_pair_blocks(cfg, n);
+    if (count <= 0) return;
+    const int n = first + count;
+    int blocks = (int)sph_pair_blocks(cfg, count);
     if (cfg.mode == SPH_PAIR_TMA)
         k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                                    (const uint16_t*)nlist, ncount, ctaRows, velOut, n);
+                                                                    (const uint16_t*)nlist, ncount, ctaRows, velOut, first, n);
     else
         k_force_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                         (const uint32_t*)nlist, ncount, velOut, n);
+                                                         (const uint32_t*)nlist, ncount, velOut, first, n);
     SPH_COUNT(L);
 }

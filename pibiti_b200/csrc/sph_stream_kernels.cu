@@ -20,6 +20,7 @@
 namespace {
 
 constexpr float kBndEps = 0.00001f;      // System.cu:51
+constexpr uint32_t kDeadIndex = 0xFFFFFFFFu;   // original-index value of a retired slot (slab mode)
 
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
@@ -172,9 +173,9 @@ __global__ void __launch_bounds__(256)
 k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
                  float4* __restrict__ pos, float4* __restrict__ vel,
                  uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU,
-                 uint32_t* __restrict__ cellCount, int n)
+                 uint32_t* __restrict__ cellCount, int first, int n)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p4 = pos[i], v4 = vel[i];
     float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
@@ -196,6 +197,7 @@ k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
 
     pos[i] = make_float4(p.x, p.y, p.z, p4.w);
     vel[i] = make_float4(v.x, v.y, v.z, v4.w);
+    if (!cellCount) return;                 // slab mode: hashing happens after migration and halo exchange
 
     uint32_t key = cell_hash(par, p);
     // The hard clamp keeps every finite particle inside the grid.  A NaN position is undefined
@@ -278,7 +280,7 @@ k_scan_tiles(uint32_t* __restrict__ tileSums, int numTiles, uint32_t* __restrict
 
 __global__ void __launch_bounds__(256)
 k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ tileSums,
-             uint32_t* __restrict__ maxCount, int numCells)
+             uint32_t* __restrict__ maxCount, int numCells, int maxCells)
 {
     __shared__ uint32_t total;
     const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
@@ -301,7 +303,7 @@ k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const
         }
     }
     #pragma unroll
-    for (int k = 0; k < 16; k++) { s += c[k]; mx = max(mx, c[k]); }
+    for (int k = 0; k < 16; k++) { s += c[k]; if (base + k < maxCells) mx = max(mx, c[k]); }
     uint32_t ex = block_excl_scan_256(s, &total) + tileSums[blockIdx.x];
     uint32_t o[16];
     #pragma unroll
@@ -354,7 +356,8 @@ k_rank_gather(const uint2* __restrict__ pairT, const uint32_t* __restrict__ keyU
     uint32_t key = keyU[me.x];
     uint32_t s = cellStart[key], e = cellStart[key + 1];
     uint32_t r = 0;
-    for (uint32_t t = s; t < e; t++) r += (pairT[t].y < me.y) ? 1u : 0u;
+    if (me.y == kDeadIndex) r = (uint32_t)d - s;            // slab mode: retired slots, order irrelevant
+    else for (uint32_t t = s; t < e; t++) r += (pairT[t].y < me.y) ? 1u : 0u;
     uint32_t f = s + r;
     float4 p = posIn[me.x], v = velIn[me.x];
     posOut[f] = p;
@@ -412,6 +415,114 @@ __global__ void k_pack_pairs(const uint32_t* __restrict__ keyS, const uint32_t* 
     if (i < n) out[i] = make_uint2(keyS[i], idx[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Slab decomposition (one handle per GPU owns the z-cell layers [zLo, zHi)).
+// Records travelling between ranks are 48 bytes: position, velocity, (original index, 0, 0, 0).
+
+struct SlabRecord { float4 pos; float4 vel; uint4 meta; };
+
+__device__ __forceinline__ int z_cell(const SimParams& par, float z)
+{
+    return (int)floorf((z - par.worldMin.z) / par.cellSize.z);
+}
+
+// owned particles [first, n): those whose z-cell left [zLo, zHi) are copied out and retired
+__global__ void __launch_bounds__(256)
+k_slab_take_leavers(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                    uint32_t* __restrict__ idx, int first, int n, int zLo, int zHi, int hasLower, int hasUpper,
+                    SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
+                    uint32_t* __restrict__ counters)
+{
+    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = idx[i];
+    if (id == kDeadIndex) return;
+    const float4 p = pos[i];
+    const int zc = z_cell(par, p.z);
+    SlabRecord* dst = nullptr;  int cap = 0;  uint32_t* ctr = nullptr;
+    if (zc < zLo && hasLower) { dst = down;  cap = capDown;  ctr = counters + 0; }
+    else if (zc >= zHi && hasUpper) { dst = up;  cap = capUp;  ctr = counters + 1; }
+    if (!dst) return;
+    const uint32_t slot = atomicAdd(ctr, 1u);
+    if (slot < (uint32_t)cap) {
+        SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(id, 0u, 0u, 0u);
+        dst[slot] = r;
+    }
+    idx[i] = kDeadIndex;
+}
+
+// copies of the live owned particles in the first / last owned layer (the neighbours' ghosts)
+__global__ void __launch_bounds__(256)
+k_slab_boundary(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                const uint32_t* __restrict__ idx, int n, int zLo, int zHi, int hasLower, int hasUpper,
+                SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
+                uint32_t* __restrict__ counters)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = idx[i];
+    if (id == kDeadIndex) return;
+    const float4 p = pos[i];
+    const int zc = z_cell(par, p.z);
+    if (zc < zLo || zc >= zHi) return;              // a ghost left over in the work set: not ours to export
+    SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(id, 0u, 0u, 0u);
+    if (zc == zLo && hasLower) {
+        uint32_t slot = atomicAdd(counters + 2, 1u);
+        if (slot < (uint32_t)capDown) down[slot] = r;
+    }
+    if (zc == zHi - 1 && hasUpper) {
+        uint32_t slot = atomicAdd(counters + 3, 1u);
+        if (slot < (uint32_t)capUp) up[slot] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_append(const SlabRecord* __restrict__ recs, int count, float4* __restrict__ pos, float4* __restrict__ vel,
+              uint32_t* __restrict__ idx, int at)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    SlabRecord r = recs[i];
+    pos[at + i] = r.pos;  vel[at + i] = r.vel;  idx[at + i] = r.meta.x;
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_export(const float4* __restrict__ pos, const float4* __restrict__ vel, const uint32_t* __restrict__ idx,
+              const float4* __restrict__ posP, const float4* __restrict__ velD, int first, int count, SlabRecord* __restrict__ recs)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    SlabRecord r;  r.pos = pos[first + i];  r.vel = vel[first + i];
+    // after a step the spare words carry density and pressure (ignored when a record is imported)
+    r.meta = make_uint4(idx[first + i], posP ? __float_as_uint(velD[first + i].w) : 0u, posP ? __float_as_uint(posP[first + i].w) : 0u, 0u);
+    recs[i] = r;
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, int first, int n)
+{
+    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// hash + histogram of the work set [0, n): local key = global hash - keyOffset; retired slots and anything
+// outside the local table go to the dummy cell numCellsLocal, which sorts behind every real cell
+__global__ void __launch_bounds__(256)
+k_slab_hash_hist(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const uint32_t* __restrict__ idx,
+                 uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU, uint32_t* __restrict__ cellCount,
+                 int n, long long keyOffset, int numCellsLocal)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = (uint32_t)numCellsLocal;
+    if (idx[i] != kDeadIndex) {
+        const float4 p = pos[i];
+        long long k = (long long)cell_hash(par, make_float3(p.x, p.y, p.z)) - keyOffset;
+        if (k >= 0 && k < (long long)numCellsLocal) key = (uint32_t)k;
+    }
+    keyU[i] = key;
+    rankU[i] = atomicAdd(&cellCount[key], 1u);
+}
+
 inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
 }  // namespace
@@ -419,21 +530,22 @@ inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 #define SPH_COUNT(L) do { if ((L).launches) ++*(L).launches; } while (0)
 
 void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel,
-                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n)
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int first, int count)
 {
+    if (count <= 0) return;
     BoundaryCtx ctx;
     ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
-    k_integrate_hash<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, keyU, rankU, cellCount, n);
+    k_integrate_hash<<<blocks_for(count, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, keyU, rankU, cellCount, first, first + count);
     SPH_COUNT(L);
 }
 
 void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* tileSums,
-                     uint32_t* maxCount, int numCells)
+                     uint32_t* maxCount, int numCells, int maxCells)
 {
     int tiles = blocks_for(numCells, SPH_SCAN_TILE);
     k_scan_reduce<<<tiles, 256, 0, L.stream>>>(cellCount, tileSums, numCells);          SPH_COUNT(L);
     k_scan_tiles<<<1, 256, 0, L.stream>>>(tileSums, tiles, maxCount);                   SPH_COUNT(L);
-    k_scan_apply<<<tiles, 256, 0, L.stream>>>(cellCount, cellStart, tileSums, maxCount, numCells);  SPH_COUNT(L);
+    k_scan_apply<<<tiles, 256, 0, L.stream>>>(cellCount, cellStart, tileSums, maxCount, numCells, maxCells);  SPH_COUNT(L);
 }
 
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
@@ -478,4 +590,55 @@ void sph_launch_cell_table_dump(const SphLaunch& L, const uint32_t* cellStart, u
 void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint32_t* idx, uint2* out, int n)
 {
     k_pack_pairs<<<blocks_for(n, 256), 256, 0, L.stream>>>(keyS, idx, out, n);  SPH_COUNT(L);
+}
+
+// ---- slab mode --------------------------------------------------------------------------------
+void sph_launch_slab_take_leavers(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, uint32_t* idx,
+                                  int first, int count, int zLo, int zHi, int hasLower, int hasUpper,
+                                  void* down, int capDown, void* up, int capUp, uint32_t* counters)
+{
+    if (count <= 0) return;
+    k_slab_take_leavers<<<blocks_for(count, 256), 256, 0, L.stream>>>(par, pos, vel, idx, first, first + count, zLo, zHi, hasLower, hasUpper,
+                                                                      (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, counters);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_boundary(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, const uint32_t* idx,
+                              int n, int zLo, int zHi, int hasLower, int hasUpper,
+                              void* down, int capDown, void* up, int capUp, uint32_t* counters)
+{
+    if (n <= 0) return;
+    k_slab_boundary<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, pos, vel, idx, n, zLo, zHi, hasLower, hasUpper,
+                                                              (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, counters);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_append(const SphLaunch& L, const void* recs, int count, float4* pos, float4* vel, uint32_t* idx, int at)
+{
+    if (count <= 0) return;
+    k_slab_append<<<blocks_for(count, 256), 256, 0, L.stream>>>((const SlabRecord*)recs, count, pos, vel, idx, at);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_export(const SphLaunch& L, const float4* pos, const float4* vel, const uint32_t* idx,
+                            const float4* posP, const float4* velD, int first, int count, void* recs)
+{
+    if (count <= 0) return;
+    k_slab_export<<<blocks_for(count, 256), 256, 0, L.stream>>>(pos, vel, idx, posP, velD, first, count, (SlabRecord*)recs);
+    SPH_COUNT(L);
+}
+
+void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first, int count)
+{
+    if (count <= 0) return;
+    k_fill_u32<<<blocks_for(count, 256), 256, 0, L.stream>>>(p, v, first, first + count);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n, long long keyOffset, int numCellsLocal)
+{
+    if (n <= 0) return;
+    k_slab_hash_hist<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, pos, idx, keyU, rankU, cellCount, n, keyOffset, numCellsLocal);
+    SPH_COUNT(L);
 }

@@ -1,0 +1,419 @@
+"""Slab decomposition of the SPH step across the GPUs of one box (new in this library; the reference
+is single-GPU).
+
+The grid is cut along z into contiguous cell-layer ranges, one per rank (one process per GPU).  The
+cell hash is z-major, so every layer is a contiguous run of a rank's sorted arrays and a one-layer
+halo reproduces the reference's +-1-cell search exactly.  One step (see include/sph_b200.h,
+"slab decomposition"):
+
+    integrate owned            -> particles that left [zLo,zHi) go to the neighbour   (exchange 1: migration)
+    first/last owned layer     -> copies become the neighbours' ghosts                (exchange 2: halo positions)
+    local stable sort by (cell hash, ORIGINAL index)  -- same order as the single-GPU sort
+    density of owned           -> (pos,p) and (vel,rho) of the boundary layers        (exchange 3: halo rho,p)
+    force of owned
+
+Every exchange is a pair of nearest-neighbour send/recv (torch.distributed batch_isend_irecv: NCCL over
+NVLink for CUDA tensors; gloo for the CPU tests).  No collective sits on the data path.
+
+`slab_step` is written over a list of ranks plus a communicator so that the same code drives
+  * one rank per process with `DistComm` (production, bench.py under torchrun), and
+  * all ranks inside one process with `LocalComm` (tests on a single GPU / on the CPU).
+The per-rank work is delegated to a backend object; `GpuSlabBackend` wraps one sph_t handle in slab mode.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import SphError
+
+REC = 12            # floats per particle record: pos xyzw, vel xyzw, (originalIndex, rho, p, 0) as raw words
+
+
+# -------------------------------------------------------------------------------------------------
+# partitioning
+def z_cells(pos: np.ndarray, par: np.ndarray) -> np.ndarray:
+    """z cell layer of each particle, in the same float32 arithmetic as the kernels."""
+    z = pos[:, 2].astype(np.float32)
+    wmin = np.float32(par["worldMin"][0][2])
+    cs = np.float32(par["cellSize"][0][2])
+    return np.floor((z - wmin) / cs).astype(np.int64)
+
+
+def cut_layers(zc: np.ndarray, grid_z: int, ranks: int, min_layers: int = 2) -> list[int]:
+    """Layer boundaries [c0=0, c1, ..., cR=grid_z] giving each rank about the same particle count."""
+    hist = np.bincount(np.clip(zc, 0, grid_z - 1), minlength=grid_z)
+    cum = np.cumsum(hist)
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, ranks):
+        target = total * r / ranks
+        c = int(np.searchsorted(cum, target, "left")) + 1
+        c = max(c, cuts[-1] + min_layers)
+        c = min(c, grid_z - min_layers * (ranks - r))
+        cuts.append(c)
+    cuts.append(grid_z)
+    if any(b - a < min_layers for a, b in zip(cuts, cuts[1:])):
+        raise SphError(f"grid has too few z layers ({grid_z}) for {ranks} slabs")
+    return cuts
+
+
+def make_records(pos: np.ndarray, vel: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    rec = np.zeros((pos.shape[0], REC), np.float32)
+    rec[:, 0:4] = pos
+    rec[:, 4:8] = vel
+    rec[:, 8] = ids.astype(np.uint32).view(np.float32)
+    return rec
+
+
+def record_ids(rec: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(rec[:, 8]).view(np.uint32)
+
+
+# -------------------------------------------------------------------------------------------------
+class GpuSlabBackend:
+    """One GPU's slab: an sph_t handle in slab mode plus its communication buffers (torch CUDA tensors)."""
+
+    def __init__(self, params: np.ndarray, capacity: int, z_lo: int, z_hi: int, has_lower: bool, has_upper: bool,
+                 device: int = 0, halo_capacity: int | None = None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        par = np.ascontiguousarray(params).copy()
+        par["numParticles"] = capacity
+        self.sys = _lib.SphSystem(par, device)
+        self.L, self.h = self.sys.lib, self.sys.h
+        self.capacity = capacity
+        self._check(self.L.sph_slab_configure(self.h, z_lo, z_hi, int(has_lower), int(has_upper)), "sph_slab_configure")
+        hc = halo_capacity or max(4096, capacity // 8)
+        self.halo_capacity = hc
+        with torch.cuda.device(self.device):
+            self.buf_down = torch.empty((hc, REC), dtype=torch.float32, device=self.device)
+            self.buf_up = torch.empty((hc, REC), dtype=torch.float32, device=self.device)
+        self.counts = (C.c_int * 4)()
+        self.n_owned = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SphError(f"{what} failed ({rc}): {self.L.sph_last_error(self.h).decode()}")
+
+    def _dev(self, x):
+        """Any record array (numpy / torch on any device) -> contiguous float32 CUDA tensor on this device."""
+        t = self.torch
+        if isinstance(x, np.ndarray):
+            x = t.from_numpy(np.ascontiguousarray(x, np.float32))
+        return x.to(self.device, dtype=t.float32).contiguous()
+
+    def set_params(self, params: np.ndarray):
+        par = np.ascontiguousarray(params).copy()
+        par["numParticles"] = self.capacity
+        self.sys.set_params(par)
+
+    def set_owned(self, records):
+        r = self._dev(records)
+        self._check(self.L.sph_slab_set_owned(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_set_owned")
+        self.sys.sync()
+        self.n_owned = r.shape[0]
+
+    def get_owned(self):
+        out = self.torch.empty((max(self.n_owned, 1), REC), dtype=self.torch.float32, device=self.device)
+        n = C.c_int(0)
+        self._check(self.L.sph_slab_get_owned(self.h, C.c_void_p(out.data_ptr()), out.shape[0], C.byref(n)), "sph_slab_get_owned")
+        return out[: n.value]
+
+    def integrate(self):
+        self._check(self.L.sph_slab_integrate(self.h), "sph_slab_integrate")
+
+    def take_leavers(self):
+        c = (C.c_int * 2)()
+        self._check(self.L.sph_slab_take_leavers(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
+                                                 C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c), "sph_slab_take_leavers")
+        return self.buf_down[: c[0]].clone(), self.buf_up[: c[1]].clone()
+
+    def add_owned(self, recs):
+        r = self._dev(recs)
+        if r.shape[0]:
+            self._check(self.L.sph_slab_add_owned(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_add_owned")
+            self.sys.sync()
+
+    def boundary_particles(self):
+        c = (C.c_int * 2)()
+        self._check(self.L.sph_slab_boundary_particles(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
+                                                       C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c),
+                    "sph_slab_boundary_particles")
+        return self.buf_down[: c[0]].clone(), self.buf_up[: c[1]].clone()
+
+    def add_ghosts(self, recs):
+        r = self._dev(recs)
+        if r.shape[0]:
+            self._check(self.L.sph_slab_add_ghosts(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_add_ghosts")
+            self.sys.sync()
+
+    def sort(self):
+        c = (C.c_int * 3)()
+        self._check(self.L.sph_slab_sort(self.h, c), "sph_slab_sort")
+        self.n_owned = c[1]
+        return c[0], c[1], c[2]
+
+    def density(self):
+        self._check(self.L.sph_slab_density(self.h), "sph_slab_density")
+
+    def boundary_dp(self):
+        c = (C.c_int * 2)()
+        # a dp row pair is 8 floats per particle; the record buffers (12 per particle) are large enough
+        self._check(self.L.sph_slab_boundary_dp(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
+                                                C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c), "sph_slab_boundary_dp")
+        return (self.buf_down.view(-1)[: 8 * c[0]].clone().view(-1, 8) if c[0] else self.buf_down[:0, :8].clone(),
+                self.buf_up.view(-1)[: 8 * c[1]].clone().view(-1, 8) if c[1] else self.buf_up[:0, :8].clone())
+
+    def set_ghost_dp(self, below, above):
+        b, a = self._dev(below), self._dev(above)
+        self._check(self.L.sph_slab_set_ghost_dp(self.h, C.c_void_p(b.data_ptr()), b.shape[0], C.c_void_p(a.data_ptr()), a.shape[0]),
+                    "sph_slab_set_ghost_dp")
+        self.sys.sync()
+
+    def force(self):
+        self._check(self.L.sph_slab_force(self.h), "sph_slab_force")
+
+    def sync(self):
+        self.sys.sync()
+
+    def empty(self, width=REC):
+        return self.torch.empty((0, width), dtype=self.torch.float32, device=self.device)
+
+
+# -------------------------------------------------------------------------------------------------
+class LocalComm:
+    """All ranks live in this process (tests): neighbour exchange is a hand-over."""
+
+    def exchange(self, outs, empties):
+        R = len(outs)
+        res = []
+        for r in range(R):
+            below = outs[r - 1][1] if r > 0 else empties[r]
+            above = outs[r + 1][0] if r < R - 1 else empties[r]
+            res.append((below, above))
+        return res
+
+
+class DistComm:
+    """One rank per process: nearest-neighbour send/recv over torch.distributed (NCCL or gloo)."""
+
+    def __init__(self, rank: int, world: int, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = rank, world
+        self.backend = dist.get_backend()
+        self.device = device if self.backend == "nccl" else torch.device("cpu")
+        self.bytes_sent = 0
+
+    def _to_wire(self, x):
+        t = self.torch
+        if isinstance(x, np.ndarray):
+            x = t.from_numpy(np.ascontiguousarray(x, np.float32))
+        return x.to(self.device).contiguous()
+
+    def exchange(self, outs, empties):
+        t, dist = self.torch, self.dist
+        (down, up), like = outs[0], empties[0]
+        width = down.shape[1] if down.ndim == 2 else up.shape[1]
+        down, up = self._to_wire(down), self._to_wire(up)
+        lower, upper = self.rank - 1, self.rank + 1
+        has_lower, has_upper = lower >= 0, upper < self.world
+        # 1. counts
+        n_out = t.tensor([down.shape[0], up.shape[0]], dtype=t.int64, device=self.device)
+        n_in = t.zeros(2, dtype=t.int64, device=self.device)
+        ops = []
+        if has_lower:
+            ops += [dist.P2POp(dist.isend, n_out[0:1], lower), dist.P2POp(dist.irecv, n_in[0:1], lower)]
+        if has_upper:
+            ops += [dist.P2POp(dist.isend, n_out[1:2], upper), dist.P2POp(dist.irecv, n_in[1:2], upper)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        n_below, n_above = (int(v) for v in n_in.tolist())
+        # 2. payload
+        below = t.empty((n_below, width), dtype=t.float32, device=self.device)
+        above = t.empty((n_above, width), dtype=t.float32, device=self.device)
+        ops = []
+        if has_lower and down.shape[0]:
+            ops.append(dist.P2POp(dist.isend, down, lower))
+        if has_lower and n_below:
+            ops.append(dist.P2POp(dist.irecv, below, lower))
+        if has_upper and up.shape[0]:
+            ops.append(dist.P2POp(dist.isend, up, upper))
+        if has_upper and n_above:
+            ops.append(dist.P2POp(dist.irecv, above, upper))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.device.type == "cuda":
+            t.cuda.current_stream().synchronize()
+        self.bytes_sent += (down.numel() + up.numel()) * 4
+        if isinstance(like, np.ndarray):
+            return [(below.cpu().numpy(), above.cpu().numpy())]
+        return [(below, above)]
+
+
+def _cat(a, b):
+    if isinstance(a, np.ndarray):
+        return np.concatenate([a, b], 0)
+    import torch
+    return torch.cat([a, b], 0)
+
+
+def slab_step(backends, comm):
+    """One SPH step of every rank in `backends` (a single rank under DistComm)."""
+    for b in backends:
+        b.integrate()
+    inc = comm.exchange([b.take_leavers() for b in backends], [b.empty() for b in backends])
+    for b, (below, above) in zip(backends, inc):
+        b.add_owned(_cat(below, above))
+    inc = comm.exchange([b.boundary_particles() for b in backends], [b.empty() for b in backends])
+    for b, (below, above) in zip(backends, inc):
+        b.add_ghosts(_cat(below, above))
+    for b in backends:
+        b.sort()
+        b.density()
+    inc = comm.exchange([b.boundary_dp() for b in backends], [b.empty(8) for b in backends])
+    for b, (below, above) in zip(backends, inc):
+        b.set_ghost_dp(below, above)
+    for b in backends:
+        b.force()
+
+
+def split_initial_state(par, pos, vel, ranks, min_layers=2):
+    """Cut the grid by particle count and return (cuts, [records of rank r])."""
+    zc = z_cells(pos, par)
+    gz = int(par["gridSize"][0][2])
+    cuts = cut_layers(zc, gz, ranks, min_layers)
+    ids = np.arange(pos.shape[0], dtype=np.uint32)
+    parts = []
+    for r in range(ranks):
+        m = (zc >= cuts[r]) & (zc < cuts[r + 1])
+        parts.append(make_records(pos[m], vel[m], ids[m]))
+    return cuts, parts
+
+
+def gather_by_id(record_arrays, n):
+    """Concatenate owned records of all ranks and order them by original index."""
+    rec = np.concatenate([np.asarray(r) for r in record_arrays], 0)
+    ids = record_ids(rec)
+    assert rec.shape[0] == n and np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "particles lost or duplicated"
+    out = np.empty_like(rec)
+    out[ids] = rec
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
+    """bench.py under torchrun: weak scaling, 8M particles per GPU, z-slab-decomposed wave tank."""
+    import torch
+    import torch.distributed as dist
+    from . import host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    title = args.workload or {1: "wave tank 8M", 2: "wave tank 16M", 4: "wave tank 32M", 8: "wave tank 64M"}[world]
+
+    s = host.CSph(device=-1)                     # scene + initial lattice on the host (every rank builds the same one)
+    s.select_scene(title)
+    par = s.params
+    pos, vel = s.host_arrays()
+    n = s.n
+    cuts, parts = split_initial_state(par, pos, vel, world)
+    mine = parts[rank]
+    del pos, vel, parts
+    halo_cap = int(par["gridSize_yx"][0]) * 24
+    capacity = int(mine.shape[0] * 1.25) + 4 * halo_cap
+    be = GpuSlabBackend(par, capacity, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, local, halo_cap)
+    be.set_owned(mine)
+    comm = DistComm(rank, world, torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(be.sys.stream())
+
+    def one_step():
+        s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
+        be.set_params(s.params)
+        slab_step([be], comm)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        one_step()
+    be.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = be.sys.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(stream)
+    be.sync()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = be.sys.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    owned = torch.tensor([be.n_owned], device="cuda", dtype=torch.int64)
+    counts = [torch.zeros_like(owned) for _ in range(world)]
+    dist.all_gather(counts, owned)
+    ms_total = float(ms.item())
+
+    # end to end with HOST buffers: every step uploads the rank's owned records from pinned memory and reads them back
+    e2e_steps = max(3, min(args.steps, 5))
+    host_rec = torch.empty((be.n_owned, REC), dtype=torch.float32, pin_memory=True)
+    host_rec.copy_(be.get_owned())
+    dist.barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        dev = host_rec.to(be.device, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        be.set_owned(dev)
+        h2d += dev.numel() * 4
+        one_step()
+        out = be.get_owned()
+        host_rec = torch.empty((out.shape[0], REC), dtype=torch.float32, pin_memory=True)
+        host_rec.copy_(out)
+        d2h += out.numel() * 4
+    be.sync()
+    dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    io = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
+    dist.all_reduce(io)
+
+    hbm, hbm_src = peaks
+    out = {
+        "metric": metric, "value": n * args.steps / (ms_total * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": title, "particles": n, "particles_per_gpu": [int(c.item()) for c in counts],
+                   "slab_cuts_z_layers": cuts, "grid": [int(x) for x in par["gridSize"][0]], "scene_file": "scenes/Scenes.xml",
+                   "parallelism": f"z-slab x{world}, 1-layer halo, NCCL send/recv",
+                   "l2": "per-GPU state is far larger than L2; no flush needed",
+                   "timing": "CUDA events on the solver stream, max over ranks", "wall_s": round(wall, 3)},
+        "clocks": clocks,
+        "e2e": {"value": n * e2e_steps / float(e2e_s.item()), "unit": unit,
+                "h2d_bytes_per_step": int(io[0].item()) // e2e_steps, "d2h_bytes_per_step": int(io[1].item()) // e2e_steps,
+                "steps": e2e_steps, "api": "per rank: owned records pinned host -> device, slab step, device -> pinned host"},
+        "gpu_launches": int(launches),
+        "halo_bytes_per_step_rank0": comm.bytes_sent // max(args.steps + warm + e2e_steps, 1),
+        "roofline": None,
+    }
+    return out
