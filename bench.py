@@ -286,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slab", action="store_true", help="N=1 through the slab path (orchestration overhead check)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -299,7 +300,7 @@ def main():
     from pibiti_b200 import build
     build.build_cuda()                                  # no-op when the in-tree .so is current
 
-    if world > 1 or args.gpus > 1:
+    if world > 1 or args.gpus > 1 or args.slab:
         from pibiti_b200 import slab
         out = slab.bench_multi(args, METRIC, UNIT, STAGE_BYTES, measured_peaks(), ClockSampler)
         if rank == 0:

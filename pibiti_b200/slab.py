@@ -267,24 +267,48 @@ def _cat(a, b):
     return torch.cat([a, b], 0)
 
 
-def slab_step(backends, comm):
-    """One SPH step of every rank in `backends` (a single rank under DistComm)."""
+def slab_step(backends, comm, prof: dict | None = None):
+    """One SPH step of every rank in `backends` (a single rank under DistComm).
+    `prof`, if given, accumulates host wall time per phase (each phase ends in a stream sync)."""
+    t = [time.perf_counter()]
+
+    def lap(name):
+        if prof is not None:
+            now = time.perf_counter()
+            prof[name] = prof.get(name, 0.0) + now - t[0]
+            t[0] = now
+
     for b in backends:
         b.integrate()
-    inc = comm.exchange([b.take_leavers() for b in backends], [b.empty() for b in backends])
+    outs = [b.take_leavers() for b in backends]
+    lap("integrate+leavers")
+    inc = comm.exchange(outs, [b.empty() for b in backends])
+    lap("exchange migration")
     for b, (below, above) in zip(backends, inc):
         b.add_owned(_cat(below, above))
-    inc = comm.exchange([b.boundary_particles() for b in backends], [b.empty() for b in backends])
+    outs = [b.boundary_particles() for b in backends]
+    lap("append+boundary")
+    inc = comm.exchange(outs, [b.empty() for b in backends])
+    lap("exchange halo")
     for b, (below, above) in zip(backends, inc):
         b.add_ghosts(_cat(below, above))
     for b in backends:
         b.sort()
+    lap("ghosts+sort")
+    for b in backends:
         b.density()
-    inc = comm.exchange([b.boundary_dp() for b in backends], [b.empty(8) for b in backends])
+    outs = [b.boundary_dp() for b in backends]
+    lap("density+boundary rho,p")
+    inc = comm.exchange(outs, [b.empty(8) for b in backends])
+    lap("exchange rho,p")
     for b, (below, above) in zip(backends, inc):
         b.set_ghost_dp(below, above)
     for b in backends:
         b.force()
+    if prof is not None:
+        for b in backends:
+            b.sync()
+    lap("force")
 
 
 def split_initial_state(par, pos, vel, ranks, min_layers=2):
@@ -323,6 +347,7 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     torch.cuda.set_device(local)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.barrier()
     title = args.workload or {1: "wave tank 8M", 2: "wave tank 16M", 4: "wave tank 32M", 8: "wave tank 64M"}[world]
 
     s = host.CSph(device=-1)                     # scene + initial lattice on the host (every rank builds the same one)
@@ -340,10 +365,12 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     comm = DistComm(rank, world, torch.device("cuda", local))
     stream = torch.cuda.ExternalStream(be.sys.stream())
 
+    prof = {} if os.environ.get("SPH_SLAB_PROFILE") else None
+
     def one_step():
         s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
         be.set_params(s.params)
-        slab_step([be], comm)
+        slab_step([be], comm, prof)
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -414,6 +441,7 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
                 "steps": e2e_steps, "api": "per rank: owned records pinned host -> device, slab step, device -> pinned host"},
         "gpu_launches": int(launches),
         "halo_bytes_per_step_rank0": comm.bytes_sent // max(args.steps + warm + e2e_steps, 1),
+        "phase_ms_rank0": {k: round(v * 1e3 / (args.steps + warm + e2e_steps), 3) for k, v in prof.items()} if prof else None,
         "roofline": None,
     }
     return out
