@@ -420,7 +420,8 @@ extern "C" int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int 
     b.lowLayers = b.hasLower;  b.highLayers = b.hasUpper;
     b.keyOffset = (long long)(zLo - b.lowLayers) * s->par.gridSize_yx;
     b.numCellsLocal = (int)s->par.gridSize_yx * (zHi - zLo + b.lowLayers + b.highLayers);
-    if (b.numCellsLocal + 1 > s->cellsAlloc) return fail(s, SPH_ERR_PARAMS, "sph_slab_configure: local cell table exceeds the allocation");
+    // the tables hold cellsAlloc+16 entries: room for the dummy cell behind the local cells
+    if (b.numCellsLocal > s->cellsAlloc) return fail(s, SPH_ERR_PARAMS, "sph_slab_configure: local cell table exceeds the allocation");
     b.first = b.count = b.work = 0;  b.sorted = false;
     b.parLocal = s->par;
     b.parLocal.numCells = (uint)b.numCellsLocal;
