@@ -118,24 +118,29 @@ const char* sph_version(void);
  * run of the sorted arrays.  The handle is created with numParticles = local CAPACITY (owned + ghosts);
  * all pointers below are DEVICE pointers on the handle's device; the caller moves the buffers between
  * ranks (pibiti_b200/slab.py does it with torch.distributed send/recv over NCCL).  One step is
- *   integrate -> take_leavers -> [exchange] -> add_owned -> boundary_particles -> [exchange] -> add_ghosts
- *   -> sort -> density -> boundary_dp -> [exchange] -> set_ghost_dp -> force
- * Particle records are SPH_SLAB_RECORD_FLOATS floats: pos xyzw, vel xyzw, (originalIndex as uint32, 0, 0, 0).
- * Density/pressure records are 8 floats per particle: all (x,y,z,pressure) rows, then all (vx,vy,vz,density) rows.
- * Functions returning counts synchronise the stream. */
+ *   integrate -> pack -> [exchange 1: fixed-size messages] -> unpack -> sort -> density
+ *             -> pack_dp -> [exchange 2: sizes known on both sides] -> unpack_dp -> force
+ * Only sph_slab_sort synchronises the stream (one read-back per step); everything else is asynchronous.
+ *
+ * Particle records are SPH_SLAB_RECORD_FLOATS floats: pos xyzw, vel xyzw, (originalIndex as uint32, rho, p, 0).
+ * A message is (1 + capL + capB) records: row 0 is a header of uint32 words {nLeavers, nBoundary, 0, ...};
+ * rows [1, 1+capL) are particles that left towards the receiver (they become OWNED there); rows
+ * [1+capL, 1+capL+capB) are copies of the sender's boundary layer (they become GHOSTS there).  The sender's
+ * own leavers are also its ghosts on that side, so sph_slab_unpack takes the outgoing messages back as well.
+ * A density/pressure message is n x (x,y,z,pressure) followed by n x (vx,vy,vz,density). */
 #define SPH_SLAB_RECORD_FLOATS 12
 int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int hasUpper);
 int sph_slab_set_owned(sph_t* s, const float* d_records, int count);            /* replaces all owned particles */
-int sph_slab_get_owned(sph_t* s, float* d_records, int capacity, int* count);
+int sph_slab_get_owned(sph_t* s, float* d_records, int capacity, int* count);    /* blocking */
 int sph_slab_integrate(sph_t* s);
-int sph_slab_take_leavers(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
-int sph_slab_add_owned(sph_t* s, const float* d_records, int count);
-int sph_slab_boundary_particles(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
-int sph_slab_add_ghosts(sph_t* s, const float* d_records, int count);
-int sph_slab_sort(sph_t* s, int* counts3 /* ghosts below, owned, ghosts above */);
+int sph_slab_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int capL, int capB);
+int sph_slab_unpack(sph_t* s, const float* d_inBelow, const float* d_inAbove,
+                    const float* d_ownDown, const float* d_ownUp, int capL, int capB);
+int sph_slab_sort(sph_t* s, int* counts3 /* ghosts below, owned, ghosts above */);    /* blocking */
 int sph_slab_density(sph_t* s);
-int sph_slab_boundary_dp(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2);
-int sph_slab_set_ghost_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove);
+int sph_slab_pack_dp(sph_t* s, float* d_down, float* d_up, int capRows, int* counts2 /* rows down, rows up */);
+int sph_slab_ghost_counts(sph_t* s, int* counts2 /* rows expected from below, from above */);
+int sph_slab_unpack_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove);
 int sph_slab_force(sph_t* s);
 
 #ifdef __cplusplus

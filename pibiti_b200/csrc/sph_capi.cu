@@ -41,6 +41,8 @@ struct sph_system {
         int g0 = 0, g1 = 0, g2 = 0;         // after sort: ghosts below [0,g0), owned [g0,g1), ghosts above [g1,g2)
         int bLoEnd = 0, bHiStart = 0;       // first owned layer [g0,bLoEnd), last owned layer [bHiStart,g1)
         bool sorted = false;
+        bool unpacked = false;             // sph_slab_unpack ran: the work-set size lives on the device
+        int workBound = 0;                  // launch bound for kernels over the work set
         SimParams parLocal;                 // par with numCells = numCellsLocal, for the neighbour walk
     } slab;
     uint32_t* counters = nullptr;           // device: 4 append counters
@@ -399,14 +401,6 @@ extern "C" void* sph_cuda_stream(sph_t* s) { return s ? (void*)s->stream : nullp
     if (!(s)->slab.on) return fail((s), SPH_ERR_STATE, "handle is not in slab mode (sph_slab_configure)"); \
     CU_TRY((s), cudaSetDevice((s)->device));
 
-static int slab_read_counters(sph_system* s, int firstCounter, int* out2)
-{
-    CU_TRY(s, cudaMemcpyAsync(s->hostInts, s->counters + firstCounter, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
-    out2[0] = (int)s->hostInts[0];  out2[1] = (int)s->hostInts[1];
-    return SPH_OK;
-}
-
 extern "C" int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int hasUpper)
 {
     if (!s) return SPH_ERR_ARG;
@@ -434,7 +428,7 @@ extern "C" int sph_slab_set_owned(sph_t* s, const float* d_records, int count)
     SLAB_CHECK(s);
     if (count < 0 || count > s->nAlloc) return fail(s, SPH_ERR_ARG, "sph_slab_set_owned: %d particles exceed capacity %d", count, s->nAlloc);
     sph_launch_slab_append(launcher(s), d_records, count, s->pos[s->cur], s->vel, s->idx[s->cur], 0);
-    s->slab.first = 0;  s->slab.count = count;  s->slab.work = count;  s->slab.sorted = false;
+    s->slab.first = 0;  s->slab.count = count;  s->slab.work = count;  s->slab.sorted = false;  s->slab.unpacked = false;
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
 }
@@ -461,56 +455,51 @@ extern "C" int sph_slab_integrate(sph_t* s)
     sph_launch_fill_u32(L, s->idx[s->cur], SPH_DEAD_INDEX, b.first + b.count, b.work - (b.first + b.count));
     b.work = b.first + b.count;
     sph_launch_integrate_hash(L, s->par, s->pos[s->cur], s->vel, nullptr, nullptr, nullptr, b.first, b.count);
-    CU_TRY(s, cudaMemsetAsync(s->counters, 0, 4 * sizeof(uint32_t), s->stream));
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
 }
 
-extern "C" int sph_slab_take_leavers(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+// device words used by the slab phases: counters[4] = work-set size, counters[5] = overflow flag
+static const int kDevWork = 4, kDevOverflow = 5;
+
+extern "C" int sph_slab_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int capL, int capB)
 {
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
-    sph_launch_slab_take_leavers(launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.first, b.count,
-                                 b.zLo, b.zHi, b.hasLower, b.hasUpper, d_down, capDown, d_up, capUp, s->counters);
-    if (int rc = slab_read_counters(s, 0, counts2)) return rc;
-    if (counts2[0] > capDown || counts2[1] > capUp)
-        return fail(s, SPH_ERR_ARG, "sph_slab_take_leavers: %d/%d leavers exceed the buffers (%d/%d)", counts2[0], counts2[1], capDown, capUp);
-    return SPH_OK;
-}
-
-static int slab_append(sph_system* s, const float* d_records, int count, const char* who)
-{
-    sph_system::Slab& b = s->slab;
-    if (count < 0 || b.work + count > s->nAlloc)
-        return fail(s, SPH_ERR_ARG, "%s: work set %d + %d exceeds capacity %d", who, b.work, count, s->nAlloc);
-    sph_launch_slab_append(launcher(s), d_records, count, s->pos[s->cur], s->vel, s->idx[s->cur], b.work);
-    b.work += count;
+    if (!d_msgDown || !d_msgUp || capL < 1 || capB < 1) return SPH_ERR_ARG;
+    SphLaunch L = launcher(s);
+    // header rows (48 bytes) hold the two append counters of each message
+    CU_TRY(s, cudaMemsetAsync(d_msgDown, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+    CU_TRY(s, cudaMemsetAsync(d_msgUp, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+    uint32_t* hd = reinterpret_cast<uint32_t*>(d_msgDown);
+    uint32_t* hu = reinterpret_cast<uint32_t*>(d_msgUp);
+    float* leavDown = d_msgDown + SPH_SLAB_RECORD_FLOATS;
+    float* leavUp = d_msgUp + SPH_SLAB_RECORD_FLOATS;
+    float* bndDown = d_msgDown + (size_t)SPH_SLAB_RECORD_FLOATS * (1 + capL);
+    float* bndUp = d_msgUp + (size_t)SPH_SLAB_RECORD_FLOATS * (1 + capL);
+    sph_launch_slab_take_leavers(L, s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.first, b.count,
+                                 b.zLo, b.zHi, b.hasLower, b.hasUpper, leavDown, capL, leavUp, capL, hd + 0, hu + 0);
+    sph_launch_slab_boundary(L, s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.work, b.zLo, b.zHi,
+                             b.hasLower, b.hasUpper, bndDown, capB, bndUp, capB, hd + 1, hu + 1);
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
 }
 
-extern "C" int sph_slab_add_owned(sph_t* s, const float* d_records, int count)
-{
-    SLAB_CHECK(s);
-    return slab_append(s, d_records, count, "sph_slab_add_owned");
-}
-
-extern "C" int sph_slab_boundary_particles(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+extern "C" int sph_slab_unpack(sph_t* s, const float* d_inBelow, const float* d_inAbove,
+                               const float* d_ownDown, const float* d_ownUp, int capL, int capB)
 {
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
-    sph_launch_slab_boundary(launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.work, b.zLo, b.zHi,
-                             b.hasLower, b.hasUpper, d_down, capDown, d_up, capUp, s->counters);
-    if (int rc = slab_read_counters(s, 2, counts2)) return rc;
-    if (counts2[0] > capDown || counts2[1] > capUp)
-        return fail(s, SPH_ERR_ARG, "sph_slab_boundary_particles: %d/%d exceed the buffers (%d/%d)", counts2[0], counts2[1], capDown, capUp);
+    CU_TRY(s, cudaMemsetAsync(s->counters + kDevOverflow, 0, sizeof(uint32_t), s->stream));
+    sph_launch_slab_unpack(launcher(s), b.hasLower ? d_inBelow : nullptr, b.hasUpper ? d_inAbove : nullptr,
+                           b.hasLower ? d_ownDown : nullptr, b.hasUpper ? d_ownUp : nullptr, capL, capB,
+                           s->pos[s->cur], s->vel, s->idx[s->cur], b.work, s->nAlloc, s->counters + kDevWork);
+    // upper bound of the work set until the sort reads the real size back
+    long long bound = (long long)b.work + 4LL * capL + 2LL * capB;
+    b.workBound = (int)(bound < s->nAlloc ? bound : s->nAlloc);
+    b.unpacked = true;
+    CU_TRY(s, cudaGetLastError());
     return SPH_OK;
-}
-
-extern "C" int sph_slab_add_ghosts(sph_t* s, const float* d_records, int count)
-{
-    SLAB_CHECK(s);
-    return slab_append(s, d_records, count, "sph_slab_add_ghosts");
 }
 
 extern "C" int sph_slab_sort(sph_t* s, int* counts3)
@@ -518,21 +507,35 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
     SphLaunch L = launcher(s);
-    const int in = s->cur, outb = s->cur ^ 1, W = b.work, CL = b.numCellsLocal;
+    const int in = s->cur, outb = s->cur ^ 1, CL = b.numCellsLocal;
     const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
-    sph_launch_slab_hash_hist(L, s->par, s->pos[in], s->idx[in], s->keyU, s->rankU, s->cellCount, W, b.keyOffset, CL);
+    if (!b.unpacked) {      // no exchange happened (single slab or first use): the work set is what the host knows
+        uint32_t w = (uint32_t)b.work;
+        CU_TRY(s, cudaMemcpyAsync(s->counters + kDevWork, &w, sizeof w, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(s, cudaMemsetAsync(s->counters + kDevOverflow, 0, sizeof(uint32_t), s->stream));
+        CU_TRY(s, cudaStreamSynchronize(s->stream));
+        b.workBound = b.work;
+    }
+    const int W = b.workBound;
+    const uint32_t* nDev = s->counters + kDevWork;
+    sph_launch_slab_hash_hist(L, s->par, s->pos[in], s->idx[in], s->keyU, s->rankU, s->cellCount, W, nDev, b.keyOffset, CL);
     sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL);
-    sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, W);
-    sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W);
-    // five cell-table entries bracket the ghost / owned / boundary-layer ranges
+    if (W > 0) {
+        sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, W, nDev);
+        sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W, nDev);
+    }
+    // one read-back: five cell-table entries bracket the ghost / owned / boundary-layer ranges, plus size and overflow
     const int cells[5] = {b.lowLayers * yx, (b.lowLayers + nz) * yx, CL, (b.lowLayers + 1) * yx, (b.lowLayers + nz - 1) * yx};
     for (int k = 0; k < 5; k++)
         CU_TRY(s, cudaMemcpyAsync(s->hostInts + k, s->cellStart + cells[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->hostInts + 5, s->counters + kDevWork, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->hostInts[6])
+        return fail(s, SPH_ERR_ARG, "slab exchange overflow: a message section or the particle capacity (%d) was too small", s->nAlloc);
     b.g0 = (int)s->hostInts[0];  b.g1 = (int)s->hostInts[1];  b.g2 = (int)s->hostInts[2];
     b.bLoEnd = (int)s->hostInts[3];  b.bHiStart = (int)s->hostInts[4];
     s->cur = outb;
-    b.first = b.g0;  b.count = b.g1 - b.g0;  b.work = W;  b.sorted = true;
+    b.first = b.g0;  b.count = b.g1 - b.g0;  b.work = (int)s->hostInts[5];  b.sorted = true;  b.unpacked = false;
     if (counts3) { counts3[0] = b.g0;  counts3[1] = b.g1 - b.g0;  counts3[2] = b.g2 - b.g1; }
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
@@ -549,13 +552,14 @@ extern "C" int sph_slab_density(sph_t* s)
     return SPH_OK;
 }
 
-extern "C" int sph_slab_boundary_dp(sph_t* s, float* d_down, int capDown, float* d_up, int capUp, int* counts2)
+// rows of the first / last owned layer: nDown x (x,y,z,p) then nDown x (vx,vy,vz,rho); asynchronous
+extern "C" int sph_slab_pack_dp(sph_t* s, float* d_down, float* d_up, int capRows, int* counts2)
 {
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
-    if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_boundary_dp: call sph_slab_sort first");
+    if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_pack_dp: call sph_slab_sort first");
     const int nDown = b.hasLower ? b.bLoEnd - b.g0 : 0, nUp = b.hasUpper ? b.g1 - b.bHiStart : 0;
-    if (nDown > capDown || nUp > capUp) return fail(s, SPH_ERR_ARG, "sph_slab_boundary_dp: %d/%d exceed the buffers", nDown, nUp);
+    if (nDown > capRows || nUp > capRows) return fail(s, SPH_ERR_ARG, "sph_slab_pack_dp: %d/%d rows exceed the buffers (%d)", nDown, nUp, capRows);
     if (nDown > 0) {
         CU_TRY(s, cudaMemcpyAsync(d_down, s->posP + b.g0, (size_t)nDown * 16, cudaMemcpyDeviceToDevice, s->stream));
         CU_TRY(s, cudaMemcpyAsync(d_down + 4 * (size_t)nDown, s->velD + b.g0, (size_t)nDown * 16, cudaMemcpyDeviceToDevice, s->stream));
@@ -564,17 +568,23 @@ extern "C" int sph_slab_boundary_dp(sph_t* s, float* d_down, int capDown, float*
         CU_TRY(s, cudaMemcpyAsync(d_up, s->posP + b.bHiStart, (size_t)nUp * 16, cudaMemcpyDeviceToDevice, s->stream));
         CU_TRY(s, cudaMemcpyAsync(d_up + 4 * (size_t)nUp, s->velD + b.bHiStart, (size_t)nUp * 16, cudaMemcpyDeviceToDevice, s->stream));
     }
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
     counts2[0] = nDown;  counts2[1] = nUp;
     return SPH_OK;
 }
 
-extern "C" int sph_slab_set_ghost_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove)
+extern "C" int sph_slab_ghost_counts(sph_t* s, int* counts2)
+{
+    SLAB_CHECK(s);
+    counts2[0] = s->slab.g0;  counts2[1] = s->slab.g2 - s->slab.g1;
+    return SPH_OK;
+}
+
+extern "C" int sph_slab_unpack_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove)
 {
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
     if (nBelow != b.g0 || nAbove != b.g2 - b.g1)
-        return fail(s, SPH_ERR_ARG, "sph_slab_set_ghost_dp: got %d/%d rows for %d/%d ghosts (ghost sets out of step between ranks)",
+        return fail(s, SPH_ERR_ARG, "sph_slab_unpack_dp: got %d/%d rows for %d/%d ghosts (ghost sets out of step between ranks)",
                     nBelow, nAbove, b.g0, b.g2 - b.g1);
     if (nBelow > 0) {
         CU_TRY(s, cudaMemcpyAsync(s->posP, d_below, (size_t)nBelow * 16, cudaMemcpyDeviceToDevice, s->stream));

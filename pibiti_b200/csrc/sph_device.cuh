@@ -37,10 +37,11 @@ void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4*
 void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* blockSums,
                      uint32_t* maxCount, int numCells, int maxCells);
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
-                       const uint32_t* cellStart, uint2* pairT, int n);
+                       const uint32_t* cellStart, uint2* pairT, int n, const uint32_t* nDev = nullptr);
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
                             const float4* posIn, const float4* velIn,
-                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n);
+                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n,
+                            const uint32_t* nDev = nullptr);     // nDev: element count read on the device (n = launch bound)
 void sph_launch_iota(const SphLaunch& L, uint32_t* idx, int n);
 // original-order accessors: out[idx[j] - start] = src[j]  /  dst[j] = in[idx[j] - start]
 void sph_launch_unpermute4(const SphLaunch& L, const float4* src, const uint32_t* idx, float4* out, int start, int count, int n);
@@ -54,16 +55,19 @@ void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint3
 #define SPH_DEAD_INDEX 0xFFFFFFFFu
 void sph_launch_slab_take_leavers(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, uint32_t* idx,
                                   int first, int count, int zLo, int zHi, int hasLower, int hasUpper,
-                                  void* down, int capDown, void* up, int capUp, uint32_t* counters);
+                                  void* down, int capDown, void* up, int capUp, uint32_t* ctrDown, uint32_t* ctrUp);
 void sph_launch_slab_boundary(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, const uint32_t* idx,
                               int n, int zLo, int zHi, int hasLower, int hasUpper,
-                              void* down, int capDown, void* up, int capUp, uint32_t* counters);
+                              void* down, int capDown, void* up, int capUp, uint32_t* ctrDown, uint32_t* ctrUp);
 void sph_launch_slab_append(const SphLaunch& L, const void* recs, int count, float4* pos, float4* vel, uint32_t* idx, int at);
 void sph_launch_slab_export(const SphLaunch& L, const float4* pos, const float4* vel, const uint32_t* idx,
                             const float4* posP, const float4* velD, int first, int count, void* recs);
 void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first, int count);
 void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
-                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n, long long keyOffset, int numCellsLocal);
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int nMax, const uint32_t* nDev,
+                               long long keyOffset, int numCellsLocal);
+void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void* inAbove, const void* ownDown, const void* ownUp,
+                            int capL, int capB, float4* pos, float4* vel, uint32_t* idx, int work0, int capacity, uint32_t* dev);
 
 // ---- sph_pair_kernels.cu ----------------------------------------------------------------------
 // Two variants of the density/force pair, same results:

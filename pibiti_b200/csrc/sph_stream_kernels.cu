@@ -336,10 +336,10 @@ k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const
 
 __global__ void __launch_bounds__(256)
 k_bucket(const uint32_t* __restrict__ keyU, const uint32_t* __restrict__ rankU, const uint32_t* __restrict__ idxIn,
-         const uint32_t* __restrict__ cellStart, uint2* __restrict__ pairT, int n)
+         const uint32_t* __restrict__ cellStart, uint2* __restrict__ pairT, int n, const uint32_t* __restrict__ nDev)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    if (j >= (nDev ? (int)*nDev : n)) return;
     uint32_t dst = cellStart[keyU[j]] + rankU[j];
     pairT[dst] = make_uint2((uint32_t)j, idxIn[j]);
 }
@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(256)
 k_rank_gather(const uint2* __restrict__ pairT, const uint32_t* __restrict__ keyU, const uint32_t* __restrict__ cellStart,
               const float4* __restrict__ posIn, const float4* __restrict__ velIn,
               float4* __restrict__ posOut, float4* __restrict__ velOut,
-              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, int n)
+              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, int n, const uint32_t* __restrict__ nDev)
 {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n) return;
+    if (d >= (nDev ? (int)*nDev : n)) return;
     uint2 me = pairT[d];
     uint32_t key = keyU[me.x];
     uint32_t s = cellStart[key], e = cellStart[key + 1];
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256)
 k_slab_take_leavers(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const float4* __restrict__ vel,
                     uint32_t* __restrict__ idx, int first, int n, int zLo, int zHi, int hasLower, int hasUpper,
                     SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
-                    uint32_t* __restrict__ counters)
+                    uint32_t* __restrict__ ctrDown, uint32_t* __restrict__ ctrUp)
 {
     int i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -440,8 +440,8 @@ k_slab_take_leavers(const __grid_constant__ SimParams par, const float4* __restr
     const float4 p = pos[i];
     const int zc = z_cell(par, p.z);
     SlabRecord* dst = nullptr;  int cap = 0;  uint32_t* ctr = nullptr;
-    if (zc < zLo && hasLower) { dst = down;  cap = capDown;  ctr = counters + 0; }
-    else if (zc >= zHi && hasUpper) { dst = up;  cap = capUp;  ctr = counters + 1; }
+    if (zc < zLo && hasLower) { dst = down;  cap = capDown;  ctr = ctrDown; }
+    else if (zc >= zHi && hasUpper) { dst = up;  cap = capUp;  ctr = ctrUp; }
     if (!dst) return;
     const uint32_t slot = atomicAdd(ctr, 1u);
     if (slot < (uint32_t)cap) {
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256)
 k_slab_boundary(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const float4* __restrict__ vel,
                 const uint32_t* __restrict__ idx, int n, int zLo, int zHi, int hasLower, int hasUpper,
                 SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
-                uint32_t* __restrict__ counters)
+                uint32_t* __restrict__ ctrDown, uint32_t* __restrict__ ctrUp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -467,11 +467,11 @@ k_slab_boundary(const __grid_constant__ SimParams par, const float4* __restrict_
     if (zc < zLo || zc >= zHi) return;              // a ghost left over in the work set: not ours to export
     SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(id, 0u, 0u, 0u);
     if (zc == zLo && hasLower) {
-        uint32_t slot = atomicAdd(counters + 2, 1u);
+        uint32_t slot = atomicAdd(ctrDown, 1u);
         if (slot < (uint32_t)capDown) down[slot] = r;
     }
     if (zc == zHi - 1 && hasUpper) {
-        uint32_t slot = atomicAdd(counters + 3, 1u);
+        uint32_t slot = atomicAdd(ctrUp, 1u);
         if (slot < (uint32_t)capUp) up[slot] = r;
     }
 }
@@ -498,6 +498,52 @@ k_slab_export(const float4* __restrict__ pos, const float4* __restrict__ vel, co
     recs[i] = r;
 }
 
+// Message layout (both directions): row 0 = header {nLeavers, nBoundary, 0...} (uint32 words), rows [1, 1+capL) =
+// particles that leave towards the receiver (they become OWNED there), rows [1+capL, 1+capL+capB) = copies of the
+// sender's boundary layer (they become GHOSTS there).  One launch appends, behind slot work0:
+//   leavers from below, leavers from above                       -> owned arrivals
+//   boundary copies from below / above, and this rank's own leavers (now sitting in the neighbour's
+//   boundary layer, i.e. in this rank's ghost layer)             -> ghosts
+// Counts stay on the device; dev[0] receives the new work-set size, dev[1] an overflow flag.
+__global__ void __launch_bounds__(256)
+k_slab_unpack(const SlabRecord* __restrict__ inBelow, const SlabRecord* __restrict__ inAbove,
+              const SlabRecord* __restrict__ ownDown, const SlabRecord* __restrict__ ownUp, int capL, int capB,
+              float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ idx, int work0, int capacity,
+              uint32_t* __restrict__ dev)
+{
+    const SlabRecord* msg[6] = {inBelow, inAbove, inBelow, inAbove, ownDown, ownUp};
+    const int word[6] = {0, 0, 1, 1, 0, 0};                 // header word holding the section's count
+    const int row0[6] = {1, 1, 1 + capL, 1 + capL, 1, 1};   // first row of the section
+    const int cap[6]  = {capL, capL, capB, capB, capL, capL};
+    const int sec = blockIdx.y;
+    uint32_t cnt[6], off = 0, total = 0, over = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t c = msg[k] ? reinterpret_cast<const uint32_t*>(msg[k])[word[k]] : 0u;
+        if (c > (uint32_t)cap[k]) { over = 1;  c = (uint32_t)cap[k]; }
+        cnt[k] = c;
+        if (k < sec) off += c;
+        total += c;
+    }
+    if ((long long)work0 + total > capacity) over = 1;
+    if (sec == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        dev[0] = (uint32_t)min((long long)work0 + total, (long long)capacity);
+        if (over) dev[1] = 1u;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mine = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; k++) if (k == sec) mine = cnt[k];
+    if (i >= (int)mine) return;
+    const long long dst = (long long)work0 + off + i;
+    if (dst >= capacity) return;
+    const SlabRecord* src = nullptr;  int r0 = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; k++) if (k == sec) { src = msg[k];  r0 = row0[k]; }
+    const SlabRecord r = src[r0 + i];
+    pos[dst] = r.pos;  vel[dst] = r.vel;  idx[dst] = r.meta.x;
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, int first, int n)
 {
     int i = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,10 +555,10 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t v, int first, int n)
 __global__ void __launch_bounds__(256)
 k_slab_hash_hist(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const uint32_t* __restrict__ idx,
                  uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU, uint32_t* __restrict__ cellCount,
-                 int n, long long keyOffset, int numCellsLocal)
+                 const uint32_t* __restrict__ nDev, long long keyOffset, int numCellsLocal)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (int)*nDev) return;
     uint32_t key = (uint32_t)numCellsLocal;
     if (idx[i] != kDeadIndex) {
         const float4 p = pos[i];
@@ -549,16 +595,16 @@ void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStar
 }
 
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
-                       const uint32_t* cellStart, uint2* pairT, int n)
+                       const uint32_t* cellStart, uint2* pairT, int n, const uint32_t* nDev)
 {
-    k_bucket<<<blocks_for(n, 256), 256, 0, L.stream>>>(keyU, rankU, idxIn, cellStart, pairT, n);  SPH_COUNT(L);
+    k_bucket<<<blocks_for(n, 256), 256, 0, L.stream>>>(keyU, rankU, idxIn, cellStart, pairT, n, nDev);  SPH_COUNT(L);
 }
 
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
                             const float4* posIn, const float4* velIn,
-                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n)
+                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n, const uint32_t* nDev)
 {
-    k_rank_gather<<<blocks_for(n, 256), 256, 0, L.stream>>>(pairT, keyU, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, n);
+    k_rank_gather<<<blocks_for(n, 256), 256, 0, L.stream>>>(pairT, keyU, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, n, nDev);
     SPH_COUNT(L);
 }
 
@@ -595,21 +641,21 @@ void sph_launch_pack_pairs(const SphLaunch& L, const uint32_t* keyS, const uint3
 // ---- slab mode --------------------------------------------------------------------------------
 void sph_launch_slab_take_leavers(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, uint32_t* idx,
                                   int first, int count, int zLo, int zHi, int hasLower, int hasUpper,
-                                  void* down, int capDown, void* up, int capUp, uint32_t* counters)
+                                  void* down, int capDown, void* up, int capUp, uint32_t* ctrDown, uint32_t* ctrUp)
 {
     if (count <= 0) return;
     k_slab_take_leavers<<<blocks_for(count, 256), 256, 0, L.stream>>>(par, pos, vel, idx, first, first + count, zLo, zHi, hasLower, hasUpper,
-                                                                      (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, counters);
+                                                                      (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, ctrDown, ctrUp);
     SPH_COUNT(L);
 }
 
 void sph_launch_slab_boundary(const SphLaunch& L, const SimParams& par, const float4* pos, const float4* vel, const uint32_t* idx,
                               int n, int zLo, int zHi, int hasLower, int hasUpper,
-                              void* down, int capDown, void* up, int capUp, uint32_t* counters)
+                              void* down, int capDown, void* up, int capUp, uint32_t* ctrDown, uint32_t* ctrUp)
 {
     if (n <= 0) return;
     k_slab_boundary<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, pos, vel, idx, n, zLo, zHi, hasLower, hasUpper,
-                                                              (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, counters);
+                                                              (SlabRecord*)down, capDown, (SlabRecord*)up, capUp, ctrDown, ctrUp);
     SPH_COUNT(L);
 }
 
@@ -636,9 +682,20 @@ void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first,
 }
 
 void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
-                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int n, long long keyOffset, int numCellsLocal)
+                               uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int nMax, const uint32_t* nDev,
+                               long long keyOffset, int numCellsLocal)
 {
-    if (n <= 0) return;
-    k_slab_hash_hist<<<blocks_for(n, 256), 256, 0, L.stream>>>(par, pos, idx, keyU, rankU, cellCount, n, keyOffset, numCellsLocal);
+    if (nMax <= 0) return;
+    k_slab_hash_hist<<<blocks_for(nMax, 256), 256, 0, L.stream>>>(par, pos, idx, keyU, rankU, cellCount, nDev, keyOffset, numCellsLocal);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void* inAbove, const void* ownDown, const void* ownUp,
+                            int capL, int capB, float4* pos, float4* vel, uint32_t* idx, int work0, int capacity, uint32_t* dev)
+{
+    int m = capL > capB ? capL : capB;
+    dim3 grid(blocks_for(m, 256), 6);
+    k_slab_unpack<<<grid, 256, 0, L.stream>>>((const SlabRecord*)inBelow, (const SlabRecord*)inAbove, (const SlabRecord*)ownDown,
+                                              (const SlabRecord*)ownUp, capL, capB, pos, vel, idx, work0, capacity, dev);
     SPH_COUNT(L);
 }

@@ -82,9 +82,9 @@ ABI_SYMBOLS = (
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
     "sph_version",
-    "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_take_leavers",
-    "sph_slab_add_owned", "sph_slab_boundary_particles", "sph_slab_add_ghosts", "sph_slab_sort", "sph_slab_density",
-    "sph_slab_boundary_dp", "sph_slab_set_ghost_dp", "sph_slab_force",
+    "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack",
+    "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
+    "sph_slab_unpack_dp", "sph_slab_force",
 )
 
 
@@ -129,14 +129,13 @@ def load() -> C.CDLL:
     lib.sph_slab_set_owned.argtypes = [vp, vp, ci]
     lib.sph_slab_get_owned.argtypes = [vp, vp, ci, ip]
     lib.sph_slab_integrate.argtypes = [vp]
-    lib.sph_slab_take_leavers.argtypes = [vp, vp, ci, vp, ci, ip]
-    lib.sph_slab_add_owned.argtypes = [vp, vp, ci]
-    lib.sph_slab_boundary_particles.argtypes = [vp, vp, ci, vp, ci, ip]
-    lib.sph_slab_add_ghosts.argtypes = [vp, vp, ci]
+    lib.sph_slab_pack.argtypes = [vp, vp, vp, ci, ci]
+    lib.sph_slab_unpack.argtypes = [vp, vp, vp, vp, vp, ci, ci]
     lib.sph_slab_sort.argtypes = [vp, ip]
     lib.sph_slab_density.argtypes = [vp]
-    lib.sph_slab_boundary_dp.argtypes = [vp, vp, ci, vp, ci, ip]
-    lib.sph_slab_set_ghost_dp.argtypes = [vp, vp, ci, vp, ci]
+    lib.sph_slab_pack_dp.argtypes = [vp, vp, vp, ci, ip]
+    lib.sph_slab_ghost_counts.argtypes = [vp, ip]
+    lib.sph_slab_unpack_dp.argtypes = [vp, vp, ci, vp, ci]
     lib.sph_slab_force.argtypes = [vp]
     _lib = lib
     return lib

@@ -6,14 +6,17 @@ cell hash is z-major, so every layer is a contiguous run of a rank's sorted arra
 halo reproduces the reference's +-1-cell search exactly.  One step (see include/sph_b200.h,
 "slab decomposition"):
 
-    integrate owned            -> particles that left [zLo,zHi) go to the neighbour   (exchange 1: migration)
-    first/last owned layer     -> copies become the neighbours' ghosts                (exchange 2: halo positions)
+    integrate owned
+    pack: particles that left [zLo,zHi) + copies of the first/last owned layer       (exchange 1: one fixed-size
+          message per neighbour; leavers become owned there, layer copies become ghosts; a rank's own
+          leavers are also its ghosts on that side)
     local stable sort by (cell hash, ORIGINAL index)  -- same order as the single-GPU sort
-    density of owned           -> (pos,p) and (vel,rho) of the boundary layers        (exchange 3: halo rho,p)
+    density of owned           -> (pos,p) and (vel,rho) rows of the boundary layers   (exchange 2: sizes known)
     force of owned
 
 Every exchange is a pair of nearest-neighbour send/recv (torch.distributed batch_isend_irecv: NCCL over
-NVLink for CUDA tensors; gloo for the CPU tests).  No collective sits on the data path.
+NVLink, ordered on the solver's CUDA stream; gloo for the CPU tests).  No collective sits on the data path and
+the host synchronises once per step (the read-back after the sort).
 
 `slab_step` is written over a list of ranks plus a communicator so that the same code drives
   * one rank per process with `DistComm` (production, bench.py under torchrun), and
@@ -75,11 +78,31 @@ def record_ids(rec: np.ndarray) -> np.ndarray:
 
 
 # -------------------------------------------------------------------------------------------------
+class SlabCaps:
+    """Message geometry every rank agrees on: a particle message is (1 + leavers + boundary) records."""
+
+    def __init__(self, leavers: int, boundary: int):
+        self.leavers, self.boundary = int(leavers), int(boundary)
+
+    @property
+    def rows(self) -> int:
+        return 1 + self.leavers + self.boundary
+
+    @staticmethod
+    def for_state(par, pos, cuts, safety: float = 3.0, floor: int = 4096) -> "SlabCaps":
+        """Sized from the initial state: `safety` x the fullest z layer (every rank computes the same numbers)."""
+        zc = z_cells(pos, par)
+        gz = int(par["gridSize"][0][2])
+        fullest = int(np.bincount(np.clip(zc, 0, gz - 1), minlength=gz).max())
+        boundary = int(fullest * safety) + floor
+        return SlabCaps(max(boundary // 2, floor), boundary)
+
+
 class GpuSlabBackend:
-    """One GPU's slab: an sph_t handle in slab mode plus its communication buffers (torch CUDA tensors)."""
+    """One GPU's slab: an sph_t handle in slab mode plus its message buffers (torch CUDA tensors)."""
 
     def __init__(self, params: np.ndarray, capacity: int, z_lo: int, z_hi: int, has_lower: bool, has_upper: bool,
-                 device: int = 0, halo_capacity: int | None = None):
+                 device: int, caps: SlabCaps):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", device)
@@ -87,14 +110,15 @@ class GpuSlabBackend:
         par["numParticles"] = capacity
         self.sys = _lib.SphSystem(par, device)
         self.L, self.h = self.sys.lib, self.sys.h
-        self.capacity = capacity
+        self.capacity, self.caps = capacity, caps
+        self.has_lower, self.has_upper = has_lower, has_upper
         self._check(self.L.sph_slab_configure(self.h, z_lo, z_hi, int(has_lower), int(has_upper)), "sph_slab_configure")
-        hc = halo_capacity or max(4096, capacity // 8)
-        self.halo_capacity = hc
         with torch.cuda.device(self.device):
-            self.buf_down = torch.empty((hc, REC), dtype=torch.float32, device=self.device)
-            self.buf_up = torch.empty((hc, REC), dtype=torch.float32, device=self.device)
-        self.counts = (C.c_int * 4)()
+            mk = lambda: torch.zeros((caps.rows, REC), dtype=torch.float32, device=self.device)
+            self.msg_down, self.msg_up = mk(), mk()
+            self.dp_down = torch.zeros((caps.boundary, 8), dtype=torch.float32, device=self.device)
+            self.dp_up = torch.zeros((caps.boundary, 8), dtype=torch.float32, device=self.device)
+        self.stream = torch.cuda.ExternalStream(self.sys.stream(), device=self.device)
         self.n_owned = 0
 
     def _check(self, rc, what):
@@ -102,11 +126,19 @@ class GpuSlabBackend:
             raise SphError(f"{what} failed ({rc}): {self.L.sph_last_error(self.h).decode()}")
 
     def _dev(self, x):
-        """Any record array (numpy / torch on any device) -> contiguous float32 CUDA tensor on this device."""
+        """Any array (numpy / torch on any device) -> contiguous float32 CUDA tensor on this device."""
         t = self.torch
         if isinstance(x, np.ndarray):
             x = t.from_numpy(np.ascontiguousarray(x, np.float32))
-        return x.to(self.device, dtype=t.float32).contiguous()
+        if x.is_cuda and x.device == self.device and x.dtype == t.float32 and x.is_contiguous():
+            return x                    # already in place (NCCL path: produced on the solver's stream)
+        y = x.to(self.device, dtype=t.float32).contiguous()
+        t.cuda.current_stream(self.device).synchronize()    # the copy ran on torch's stream, the solver has its own
+        return y
+
+    @staticmethod
+    def _p(tensor):
+        return C.c_void_p(tensor.data_ptr())
 
     def set_params(self, params: np.ndarray):
         par = np.ascontiguousarray(params).copy()
@@ -115,66 +147,53 @@ class GpuSlabBackend:
 
     def set_owned(self, records):
         r = self._dev(records)
-        self._check(self.L.sph_slab_set_owned(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_set_owned")
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.L.sph_slab_set_owned(self.h, self._p(r), r.shape[0]), "sph_slab_set_owned")
         self.sys.sync()
         self.n_owned = r.shape[0]
 
     def get_owned(self):
         out = self.torch.empty((max(self.n_owned, 1), REC), dtype=self.torch.float32, device=self.device)
         n = C.c_int(0)
-        self._check(self.L.sph_slab_get_owned(self.h, C.c_void_p(out.data_ptr()), out.shape[0], C.byref(n)), "sph_slab_get_owned")
+        self._check(self.L.sph_slab_get_owned(self.h, self._p(out), out.shape[0], C.byref(n)), "sph_slab_get_owned")
         return out[: n.value]
 
     def integrate(self):
         self._check(self.L.sph_slab_integrate(self.h), "sph_slab_integrate")
 
-    def take_leavers(self):
-        c = (C.c_int * 2)()
-        self._check(self.L.sph_slab_take_leavers(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
-                                                 C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c), "sph_slab_take_leavers")
-        return self.buf_down[: c[0]].clone(), self.buf_up[: c[1]].clone()
+    def pack(self):
+        self._check(self.L.sph_slab_pack(self.h, self._p(self.msg_down), self._p(self.msg_up), self.caps.leavers, self.caps.boundary),
+                    "sph_slab_pack")
+        return self.msg_down, self.msg_up
 
-    def add_owned(self, recs):
-        r = self._dev(recs)
-        if r.shape[0]:
-            self._check(self.L.sph_slab_add_owned(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_add_owned")
-            self.sys.sync()
-
-    def boundary_particles(self):
-        c = (C.c_int * 2)()
-        self._check(self.L.sph_slab_boundary_particles(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
-                                                       C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c),
-                    "sph_slab_boundary_particles")
-        return self.buf_down[: c[0]].clone(), self.buf_up[: c[1]].clone()
-
-    def add_ghosts(self, recs):
-        r = self._dev(recs)
-        if r.shape[0]:
-            self._check(self.L.sph_slab_add_ghosts(self.h, C.c_void_p(r.data_ptr()), r.shape[0]), "sph_slab_add_ghosts")
-            self.sys.sync()
+    def unpack(self, below, above):
+        b, a = self._dev(below), self._dev(above)
+        self._keep = (b, a)             # the launch is asynchronous: keep the sources alive
+        self._check(self.L.sph_slab_unpack(self.h, self._p(b), self._p(a), self._p(self.msg_down), self._p(self.msg_up),
+                                           self.caps.leavers, self.caps.boundary), "sph_slab_unpack")
 
     def sort(self):
         c = (C.c_int * 3)()
         self._check(self.L.sph_slab_sort(self.h, c), "sph_slab_sort")
         self.n_owned = c[1]
+        self.ghosts = (c[0], c[2])
         return c[0], c[1], c[2]
 
     def density(self):
         self._check(self.L.sph_slab_density(self.h), "sph_slab_density")
 
-    def boundary_dp(self):
+    def pack_dp(self):
         c = (C.c_int * 2)()
-        # a dp row pair is 8 floats per particle; the record buffers (12 per particle) are large enough
-        self._check(self.L.sph_slab_boundary_dp(self.h, C.c_void_p(self.buf_down.data_ptr()), self.halo_capacity,
-                                                C.c_void_p(self.buf_up.data_ptr()), self.halo_capacity, c), "sph_slab_boundary_dp")
-        return (self.buf_down.view(-1)[: 8 * c[0]].clone().view(-1, 8) if c[0] else self.buf_down[:0, :8].clone(),
-                self.buf_up.view(-1)[: 8 * c[1]].clone().view(-1, 8) if c[1] else self.buf_up[:0, :8].clone())
+        self._check(self.L.sph_slab_pack_dp(self.h, self._p(self.dp_down), self._p(self.dp_up), self.caps.boundary, c), "sph_slab_pack_dp")
+        return self.dp_down.view(-1)[: 8 * c[0]].view(-1, 8), self.dp_up.view(-1)[: 8 * c[1]].view(-1, 8)
 
-    def set_ghost_dp(self, below, above):
+    def expected_dp(self):
+        return self.ghosts
+
+    def unpack_dp(self, below, above):
         b, a = self._dev(below), self._dev(above)
-        self._check(self.L.sph_slab_set_ghost_dp(self.h, C.c_void_p(b.data_ptr()), b.shape[0], C.c_void_p(a.data_ptr()), a.shape[0]),
-                    "sph_slab_set_ghost_dp")
-        self.sys.sync()
+        self._keep_dp = (b, a)
+        self._check(self.L.sph_slab_unpack_dp(self.h, self._p(b), b.shape[0], self._p(a), a.shape[0]), "sph_slab_unpack_dp")
 
     def force(self):
         self._check(self.L.sph_slab_force(self.h), "sph_slab_force")
@@ -182,132 +201,128 @@ class GpuSlabBackend:
     def sync(self):
         self.sys.sync()
 
-    def empty(self, width=REC):
-        return self.torch.empty((0, width), dtype=self.torch.float32, device=self.device)
+    def empty_message(self):
+        return self.torch.zeros((self.caps.rows, REC), dtype=self.torch.float32, device=self.device)
+
+    def empty_dp(self):
+        return self.torch.zeros((0, 8), dtype=self.torch.float32, device=self.device)
 
 
 # -------------------------------------------------------------------------------------------------
 class LocalComm:
-    """All ranks live in this process (tests): neighbour exchange is a hand-over."""
+    """All ranks live in this process (tests): a neighbour exchange is a hand-over."""
 
-    def exchange(self, outs, empties):
+    def exchange(self, backends, outs, empty, expected=None):
         R = len(outs)
         res = []
         for r in range(R):
-            below = outs[r - 1][1] if r > 0 else empties[r]
-            above = outs[r + 1][0] if r < R - 1 else empties[r]
+            for b in backends:
+                b.sync()
+            below = _copy(outs[r - 1][1]) if r > 0 else empty(backends[r])
+            above = _copy(outs[r + 1][0]) if r < R - 1 else empty(backends[r])
             res.append((below, above))
         return res
 
 
 class DistComm:
-    """One rank per process: nearest-neighbour send/recv over torch.distributed (NCCL or gloo)."""
+    """One rank per process: nearest-neighbour send/recv over torch.distributed.
+    NCCL: tensors stay on the GPU and the operations are ordered on the solver's stream (no host sync).
+    gloo: tensors are staged through the host (CPU tests, or several ranks sharing one GPU)."""
 
-    def __init__(self, rank: int, world: int, device=None):
+    def __init__(self, rank: int, world: int):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = rank, world
-        self.backend = dist.get_backend()
-        self.device = device if self.backend == "nccl" else torch.device("cpu")
+        self.nccl = dist.get_backend() == "nccl"
         self.bytes_sent = 0
 
-    def _to_wire(self, x):
-        t = self.torch
-        if isinstance(x, np.ndarray):
-            x = t.from_numpy(np.ascontiguousarray(x, np.float32))
-        return x.to(self.device).contiguous()
-
-    def exchange(self, outs, empties):
+    def exchange(self, backends, outs, empty, expected=None):
+        """outs[0] = (to lower, to upper).  Fixed-size messages when `expected` is None (receive buffers have the
+        senders' shape); otherwise expected[0] = (rows from below, rows from above)."""
         t, dist = self.torch, self.dist
-        (down, up), like = outs[0], empties[0]
-        width = down.shape[1] if down.ndim == 2 else up.shape[1]
-        down, up = self._to_wire(down), self._to_wire(up)
+        be, (down, up) = backends[0], outs[0]
         lower, upper = self.rank - 1, self.rank + 1
         has_lower, has_upper = lower >= 0, upper < self.world
-        # 1. counts
-        n_out = t.tensor([down.shape[0], up.shape[0]], dtype=t.int64, device=self.device)
-        n_in = t.zeros(2, dtype=t.int64, device=self.device)
-        ops = []
-        if has_lower:
-            ops += [dist.P2POp(dist.isend, n_out[0:1], lower), dist.P2POp(dist.irecv, n_in[0:1], lower)]
-        if has_upper:
-            ops += [dist.P2POp(dist.isend, n_out[1:2], upper), dist.P2POp(dist.irecv, n_in[1:2], upper)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        n_below, n_above = (int(v) for v in n_in.tolist())
-        # 2. payload
-        below = t.empty((n_below, width), dtype=t.float32, device=self.device)
-        above = t.empty((n_above, width), dtype=t.float32, device=self.device)
-        ops = []
-        if has_lower and down.shape[0]:
-            ops.append(dist.P2POp(dist.isend, down, lower))
-        if has_lower and n_below:
-            ops.append(dist.P2POp(dist.irecv, below, lower))
-        if has_upper and up.shape[0]:
-            ops.append(dist.P2POp(dist.isend, up, upper))
-        if has_upper and n_above:
-            ops.append(dist.P2POp(dist.irecv, above, upper))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if self.device.type == "cuda":
-            t.cuda.current_stream().synchronize()
-        self.bytes_sent += (down.numel() + up.numel()) * 4
-        if isinstance(like, np.ndarray):
-            return [(below.cpu().numpy(), above.cpu().numpy())]
+        as_numpy = isinstance(down, np.ndarray)
+        if as_numpy:
+            down, up = t.from_numpy(np.ascontiguousarray(down)), t.from_numpy(np.ascontiguousarray(up))
+        width = down.shape[1]
+        n_below, n_above = (down.shape[0], up.shape[0]) if expected is None else expected[0]
+        if self.nccl:
+            ctx = t.cuda.stream(be.stream)
+            dev = down.device
+        else:
+            ctx = _NullCtx()
+            if down.is_cuda:
+                be.sync()
+            down, up, dev = down.cpu(), up.cpu(), t.device("cpu")
+        with ctx:
+            below = t.zeros((n_below if has_lower else (n_below if expected is None else 0), width), dtype=t.float32, device=dev)
+            above = t.zeros((n_above if has_upper else (n_above if expected is None else 0), width), dtype=t.float32, device=dev)
+            ops = []
+            if has_lower and down.shape[0]:
+                ops.append(dist.P2POp(dist.isend, down.contiguous(), lower))
+            if has_lower and below.shape[0]:
+                ops.append(dist.P2POp(dist.irecv, below, lower))
+            if has_upper and up.shape[0]:
+                ops.append(dist.P2POp(dist.isend, up.contiguous(), upper))
+            if has_upper and above.shape[0]:
+                ops.append(dist.P2POp(dist.irecv, above, upper))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()            # NCCL: orders the stream, does not block the host
+        self.bytes_sent += (down.numel() * has_lower + up.numel() * has_upper) * 4
+        if as_numpy:
+            return [(below.numpy(), above.numpy())]
         return [(below, above)]
 
 
-def _cat(a, b):
-    if isinstance(a, np.ndarray):
-        return np.concatenate([a, b], 0)
-    import torch
-    return torch.cat([a, b], 0)
+def _copy(x):
+    return x.copy() if isinstance(x, np.ndarray) else x.clone()
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def slab_step(backends, comm, prof: dict | None = None):
     """One SPH step of every rank in `backends` (a single rank under DistComm).
-    `prof`, if given, accumulates host wall time per phase (each phase ends in a stream sync)."""
+    `prof`, if given, accumulates host wall time per phase (with a stream sync after each: profiling only)."""
     t = [time.perf_counter()]
 
     def lap(name):
         if prof is not None:
+            for b in backends:
+                b.sync()
             now = time.perf_counter()
             prof[name] = prof.get(name, 0.0) + now - t[0]
             t[0] = now
 
     for b in backends:
         b.integrate()
-    outs = [b.take_leavers() for b in backends]
-    lap("integrate+leavers")
-    inc = comm.exchange(outs, [b.empty() for b in backends])
-    lap("exchange migration")
+    outs = [b.pack() for b in backends]
+    lap("integrate+pack")
+    inc = comm.exchange(backends, outs, lambda b: b.empty_message())
+    lap("exchange particles")
     for b, (below, above) in zip(backends, inc):
-        b.add_owned(_cat(below, above))
-    outs = [b.boundary_particles() for b in backends]
-    lap("append+boundary")
-    inc = comm.exchange(outs, [b.empty() for b in backends])
-    lap("exchange halo")
-    for b, (below, above) in zip(backends, inc):
-        b.add_ghosts(_cat(below, above))
-    for b in backends:
+        b.unpack(below, above)
         b.sort()
-    lap("ghosts+sort")
+    lap("unpack+sort")
     for b in backends:
         b.density()
-    outs = [b.boundary_dp() for b in backends]
-    lap("density+boundary rho,p")
-    inc = comm.exchange(outs, [b.empty(8) for b in backends])
+    outs = [b.pack_dp() for b in backends]
+    lap("density+pack rho,p")
+    inc = comm.exchange(backends, outs, lambda b: b.empty_dp(), [b.expected_dp() for b in backends])
     lap("exchange rho,p")
     for b, (below, above) in zip(backends, inc):
-        b.set_ghost_dp(below, above)
+        b.unpack_dp(below, above)
     for b in backends:
         b.force()
-    if prof is not None:
-        for b in backends:
-            b.sync()
     lap("force")
 
 
@@ -357,13 +372,13 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     n = s.n
     cuts, parts = split_initial_state(par, pos, vel, world)
     mine = parts[rank]
-    del pos, vel, parts
-    halo_cap = int(par["gridSize_yx"][0]) * 24
-    capacity = int(mine.shape[0] * 1.25) + 4 * halo_cap
-    be = GpuSlabBackend(par, capacity, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, local, halo_cap)
+    caps = SlabCaps.for_state(par, pos, cuts)
+    capacity = int(mine.shape[0] * 1.25) + 4 * caps.rows
+    be = GpuSlabBackend(par, capacity, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, local, caps)
     be.set_owned(mine)
-    comm = DistComm(rank, world, torch.device("cuda", local))
-    stream = torch.cuda.ExternalStream(be.sys.stream())
+    del pos, vel, parts
+    comm = DistComm(rank, world)
+    stream = be.stream
 
     prof = {} if os.environ.get("SPH_SLAB_PROFILE") else None
 

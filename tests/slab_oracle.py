@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: a CPU backend for pibiti_b200.slab built on the oracle's stage functions, so
 that the slab protocol (partition, migration, halo, boundary exchange) can be exercised without a GPU.
-Same interface as pibiti_b200.slab.GpuSlabBackend; arrays are numpy."""
+Same interface and same message format as pibiti_b200.slab.GpuSlabBackend; arrays are numpy."""
 from __future__ import annotations
 
 import numpy as np
@@ -9,17 +9,42 @@ from pibiti_b200.slab import REC, record_ids, z_cells
 
 
 class OracleSlabBackend:
-    def __init__(self, oracle, params, z_lo, z_hi, has_lower, has_upper):
+    def __init__(self, oracle, params, z_lo, z_hi, has_lower, has_upper, caps):
         self.o = oracle
         self.par = np.ascontiguousarray(params).copy()
         self.z_lo, self.z_hi, self.has_lower, self.has_upper = z_lo, z_hi, has_lower, has_upper
+        self.caps = caps
         self.rec = np.zeros((0, REC), np.float32)
-        self.ghosts = np.zeros((0, REC), np.float32)
         self.n_owned = 0
 
-    def empty(self, width=REC):
-        return np.zeros((0, width), np.float32)
+    # -- helpers ---------------------------------------------------------------------------------
+    def _zc(self, rec):
+        return z_cells(rec[:, 0:4], self.par)
 
+    def _message(self, leavers, boundary):
+        c = self.caps
+        assert leavers.shape[0] <= c.leavers and boundary.shape[0] <= c.boundary, "message section overflow"
+        m = np.zeros((c.rows, REC), np.float32)
+        m[0, 0:2] = np.array([leavers.shape[0], boundary.shape[0]], np.uint32).view(np.float32)
+        m[1:1 + leavers.shape[0]] = leavers
+        m[1 + c.leavers:1 + c.leavers + boundary.shape[0]] = boundary
+        return m
+
+    def _sections(self, m):
+        c = self.caps
+        nl, nb = (int(v) for v in np.ascontiguousarray(m[0, 0:2]).view(np.uint32))
+        return m[1:1 + nl], m[1 + c.leavers:1 + c.leavers + nb]
+
+    def empty_message(self):
+        return np.zeros((self.caps.rows, REC), np.float32)
+
+    def empty_dp(self):
+        return np.zeros((0, 8), np.float32)
+
+    def sync(self):
+        pass
+
+    # -- interface -------------------------------------------------------------------------------
     def set_params(self, params):
         self.par = np.ascontiguousarray(params).copy()
 
@@ -30,41 +55,42 @@ class OracleSlabBackend:
     def get_owned(self):
         return self.rec.copy()
 
-    def _zc(self, rec):
-        return z_cells(rec[:, 0:4], self.par)
-
     def integrate(self):
         self.o.set_params(self.par)
         if self.rec.shape[0]:
             pos, vel = self.o.integrate(np.ascontiguousarray(self.rec[:, 0:4]), np.ascontiguousarray(self.rec[:, 4:8]))
             self.rec[:, 0:4], self.rec[:, 4:8] = pos, vel
 
-    def take_leavers(self):
+    def pack(self):
         zc = self._zc(self.rec)
         down = (zc < self.z_lo) & self.has_lower
         up = (zc >= self.z_hi) & self.has_upper
-        out = self.rec[down].copy(), self.rec[up].copy()
+        self.left_down, self.left_up = self.rec[down].copy(), self.rec[up].copy()
         self.rec = self.rec[~(down | up)]
-        return out
-
-    def add_owned(self, recs):
-        self.rec = np.concatenate([self.rec, np.asarray(recs, np.float32).reshape(-1, REC)], 0)
-
-    def boundary_particles(self):
         zc = self._zc(self.rec)
-        return (self.rec[(zc == self.z_lo) & self.has_lower].copy(), self.rec[(zc == self.z_hi - 1) & self.has_upper].copy())
+        bnd_down = self.rec[(zc == self.z_lo) & self.has_lower]
+        bnd_up = self.rec[(zc == self.z_hi - 1) & self.has_upper]
+        return self._message(self.left_down, bnd_down), self._message(self.left_up, bnd_up)
 
-    def add_ghosts(self, recs):
-        self.ghosts = np.asarray(recs, np.float32).reshape(-1, REC).copy()
+    def unpack(self, below, above):
+        lb, gb = self._sections(np.asarray(below, np.float32))
+        la, ga = self._sections(np.asarray(above, np.float32))
+        self.rec = np.concatenate([self.rec, lb, la], 0)
+        # ghosts: the neighbours' boundary layers plus my own leavers (they now sit in those layers)
+        self.ghosts = np.concatenate([gb, ga, self.left_down, self.left_up], 0)
 
     def sort(self):
         allr = np.concatenate([self.rec, self.ghosts], 0)
+        zc_all = self._zc(allr)
+        lo = self.z_lo - (1 if self.has_lower else 0)
+        hi = self.z_hi + (1 if self.has_upper else 0)
+        allr = allr[(zc_all >= lo) & (zc_all < hi)]              # outside the local table: dropped (dummy cell)
         self.o.set_params(self.par)
         pos = np.ascontiguousarray(allr[:, 0:4])
         vel = np.ascontiguousarray(allr[:, 4:8])
         hashes = self.o.calc_hash(pos)[:, 0]
         ids = record_ids(allr)
-        order = np.lexsort((ids, hashes)).astype(np.uint32)          # by cell hash, ties by ORIGINAL index
+        order = np.lexsort((ids, hashes)).astype(np.uint32)       # by cell hash, ties by ORIGINAL index
         pairs = np.ascontiguousarray(np.stack([hashes[order], order], 1).astype(np.uint32))
         ncell = int(self.par["numCells"][0])
         self.cell_start, self.spos, self.svel = self.o.reorder(pairs, pos, vel, ncell)
@@ -74,7 +100,8 @@ class OracleSlabBackend:
         self.pairs = np.ascontiguousarray(np.stack([hashes[order], np.arange(n, dtype=np.uint32)], 1).astype(np.uint32))
         self.owned_mask = (self.szc >= self.z_lo) & (self.szc < self.z_hi)
         self.n_owned = int(self.owned_mask.sum())
-        return int((self.szc < self.z_lo).sum()), self.n_owned, int((self.szc >= self.z_hi).sum())
+        self.ghost_counts = (int((self.szc < self.z_lo).sum()), int((self.szc >= self.z_hi).sum()))
+        return self.ghost_counts[0], self.n_owned, self.ghost_counts[1]
 
     def density(self):
         self.pres, self.dens = self.o.density(self.spos, self.pairs, self.cell_start)
@@ -87,10 +114,13 @@ class OracleSlabBackend:
         rows[:, 7] = self.dens[mask]
         return rows
 
-    def boundary_dp(self):
+    def pack_dp(self):
         return (self._dp_rows((self.szc == self.z_lo) & self.has_lower), self._dp_rows((self.szc == self.z_hi - 1) & self.has_upper))
 
-    def set_ghost_dp(self, below, above):
+    def expected_dp(self):
+        return self.ghost_counts
+
+    def unpack_dp(self, below, above):
         below, above = np.asarray(below, np.float32).reshape(-1, 8), np.asarray(above, np.float32).reshape(-1, 8)
         mb, ma = self.szc < self.z_lo, self.szc >= self.z_hi
         assert below.shape[0] == mb.sum() and above.shape[0] == ma.sum(), "ghost sets out of step between ranks"
@@ -106,7 +136,3 @@ class OracleSlabBackend:
         rec[:, 8] = self.sids[m].view(np.float32)
         rec[:, 9], rec[:, 10] = self.dens[m], self.pres[m]
         self.rec = rec
-        self.ghosts = np.zeros((0, REC), np.float32)
-
-    def sync(self):
-        pass

@@ -28,15 +28,16 @@ def main():
     pos, vel = s.host_arrays()
     vel[:, 2] = 1.5 * np.sin(np.arange(vel.shape[0], dtype=np.float32) * np.float32(0.37)).astype(np.float32)   # == test_slab.stir
     cuts, parts = slab.split_initial_state(par, pos, vel, world)
+    caps = slab.SlabCaps.for_state(par, pos, cuts)
     if kind == "oracle":
         from oracle import oracle as orc
         from slab_oracle import OracleSlabBackend
-        be = OracleSlabBackend(orc.load("port"), par, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1)
+        be = OracleSlabBackend(orc.load("port"), par, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, caps)
     else:
-        cap = int(parts[rank].shape[0] * 1.5) + 20000
-        be = slab.GpuSlabBackend(par, cap, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, 0, 20000)
+        cap = int(parts[rank].shape[0] * 1.5) + 4 * caps.rows
+        be = slab.GpuSlabBackend(par, cap, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, 0, caps)
     be.set_owned(parts[rank])
-    comm = slab.DistComm(rank, world, torch.device("cuda", 0) if kind == "gpu" else None)
+    comm = slab.DistComm(rank, world)
     for _ in range(steps):
         s.UpdateEmitter()
         be.set_params(s.params)

@@ -87,7 +87,8 @@ def test_oracle_slabs_equal_single_domain(oracle_port, title, ranks):
     steps = 8
     s, par, pos, vel = scene_state(title)
     cuts, parts = slab.split_initial_state(par, pos, vel, ranks)
-    bes = [OracleSlabBackend(oracle_port, par, cuts[r], cuts[r + 1], r > 0, r < ranks - 1) for r in range(ranks)]
+    caps = slab.SlabCaps.for_state(par, pos, cuts)
+    bes = [OracleSlabBackend(oracle_port, par, cuts[r], cuts[r + 1], r > 0, r < ranks - 1, caps) for r in range(ranks)]
     for b, p in zip(bes, parts):
         b.set_owned(p)
     comm = slab.LocalComm()
@@ -144,7 +145,8 @@ def test_gpu_slabs_equal_single_gpu(title, ranks, variant, monkeypatch):
     steps = 10
     s, par, pos, vel = scene_state(title)
     cuts, parts = slab.split_initial_state(par, pos, vel, ranks)
-    bes = [slab.GpuSlabBackend(par, int(p.shape[0] * 1.5) + 40000, cuts[r], cuts[r + 1], r > 0, r < ranks - 1, 0, 40000)
+    caps = slab.SlabCaps.for_state(par, pos, cuts)
+    bes = [slab.GpuSlabBackend(par, int(p.shape[0] * 1.5) + 4 * caps.rows, cuts[r], cuts[r + 1], r > 0, r < ranks - 1, 0, caps)
            for r, p in enumerate(parts)]
     for b, p in zip(bes, parts):
         b.set_owned(p)
