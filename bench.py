@@ -202,7 +202,7 @@ def run_ours_single(args) -> dict:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
                 "steps": e2e_steps, "api": "cSPH setArray(pos,vel) -> Update -> getArray(pos,vel), pinned host buffers"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_force (pair force)", "achieved": round(achieved, 1), "peak": hbm,
+        "roofline": {"bound": "hbm", "kernel": "k_force_l1 (pair force over neighbour lists)", "achieved": round(achieved, 1), "peak": hbm,
                      "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": TRAFFIC_BYTES.get("force"),
                      "peak_source": hbm_src, "algorithmic_bytes_per_particle": STAGE_BYTES["force"],
                      "note": "density+force are FP32/shared-memory bound, not HBM bound (SURVEY.md D7); see fp32_frac",
@@ -212,8 +212,10 @@ def run_ours_single(args) -> dict:
     return out, s
 
 
-# measured with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
-TRAFFIC_BYTES: dict = {}
+# measured with `ncu --set full` on "tank 8M drop" (profiles/r01_*_l1.txt): dram__bytes_read.sum + dram__bytes_write.sum
+# per launch.  The force kernel's traffic is ~3x its algorithmic bytes because it also streams the neighbour lists
+# (8.4M x ~27 x 4 B = 0.9 GB) that save it two thirds of its instructions.
+TRAFFIC_BYTES: dict = {"force": 1_386_462_600, "density": 1_558_815_560}
 
 
 def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> dict:

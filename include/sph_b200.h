@@ -81,6 +81,10 @@ int sph_destroy(sph_t* s);                                   /* cSPH::_FreeMem, 
 int sph_set_params(sph_t* s, const struct SimParams* params);
 int sph_get_params(sph_t* s, struct SimParams* out);
 
+/* Colour (System.cu:406-515) and dye (:519-545) are visual-only outputs of the reference's force kernel.  They
+ * are off by default (no cost in the step); when enabled every step also fills SPH_COLOR / SPH_DYE. */
+int sph_set_visual(sph_t* s, int enable);
+
 /* ---- stepping ------------------------------------------------------------------------------ */
 /* nsteps x { integrate -> hash -> sort -> reorder -> density -> force }, the stage order of
  * cSPH::Update (SPH_Update.cpp:39-80).  Asynchronous. */

@@ -29,6 +29,7 @@ NVCC_COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", st
 CUDA_UNITS = {
     "sph_stream_kernels.cu": ["-fmad=false"],     # bit-exact float evaluation vs the CPU oracle
     "sph_pair_kernels.cu": [],
+    "sph_extras_kernels.cu": [],
     "sph_capi.cu": [],
 }
 HOST_UNITS = sorted(p.name for p in (CSRC / "host").glob("*.cpp")) if (CSRC / "host").is_dir() else []

@@ -21,6 +21,7 @@ struct sph_system {
     uint32_t *idx[2] = {nullptr, nullptr}, *keyU = nullptr, *rankU = nullptr, *keyS = nullptr, *counts = nullptr;
     uint2* pairT = nullptr;
     void* nlist = nullptr;
+    float4* clr = nullptr;  float* dye = nullptr;  bool visual = false;   // colour / dye outputs (sph_set_visual)
     uint16_t* ncount = nullptr;
     uint32_t *cellCount = nullptr, *cellStart = nullptr, *tileSums = nullptr, *maxCount = nullptr, *ctaRows = nullptr;
     int cur = 0;                    // live pos/idx buffer
@@ -80,8 +81,6 @@ static const char* check_params(const SimParams* p)
     if ((unsigned long long)p->gridSize.x * p->gridSize.y != p->gridSize_yx) return "gridSize_yx != gridSize.y*gridSize.x";
     if ((unsigned long long)p->gridSize_yx * p->gridSize.z != p->numCells) return "numCells != gridSize.x*y*z";
     if (p->numCells > 0x7fffff00u) return "numCells too large";
-    if (p->iHmap > 0) return "height-map obstacles (iHmap>0) are not implemented yet";
-    if (p->rotType > 0) return "rotor obstacles (rotType>0) are not implemented yet";
     return nullptr;
 }
 
@@ -99,7 +98,7 @@ extern "C" int sph_destroy(sph_t* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
-                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters};
+                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->clr, s->dye};
     for (void* b : bufs) if (b) cudaFree(b);
     if (s->hostInts) cudaFreeHost(s->hostInts);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -225,6 +224,10 @@ extern "C" int sph_step(sph_t* s, int nsteps)
         if (tm) cudaEventRecord(s->ev[4], s->stream);
         sph_launch_force(L, s->cfg, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
                          s->nlist, s->ncount, s->ctaRows, s->vel, 0, n);
+        if (sph_needs_obstacles(s->par)) sph_launch_obstacles(L, s->par, s->posP, s->velD, s->vel, 0, n);
+        if (s->visual)
+            sph_launch_color_dye(L, s->par, s->pos[outb], s->velS, s->velD, s->vel, s->keyS, s->cellStart, s->idx[outb],
+                                 s->clr, s->dye, 0, n);
         if (tm) cudaEventRecord(s->ev[5], s->stream);
         s->cur = outb;
         s->stepped = true;
@@ -289,9 +292,30 @@ extern "C" int sph_get_array_device(sph_t* s, int which, float* d_out, int start
     case SPH_PRESSURE:
         if (!s->stepped) return fail(s, SPH_ERR_STATE, "pressure is only defined after a step");
         sph_launch_unpermute_w(L, s->posP, s->idx[s->cur], d_out, start, count, n); break;
+    case SPH_COLOR:
+    case SPH_DYE: {
+        if (!s->visual || !s->stepped) return fail(s, SPH_ERR_STATE, "colour / dye need sph_set_visual(s, 1) and a step");
+        const void* src = which == SPH_COLOR ? (const void*)(s->clr + start) : (const void*)(s->dye + start);
+        CU_TRY(s, cudaMemcpyAsync(d_out, src, (size_t)count * (which == SPH_COLOR ? 16 : 4), cudaMemcpyDeviceToDevice, s->stream));
+        break;
+    }
     default: return fail(s, SPH_ERR_ARG, "sph_get_array: array %d not available", which);
     }
     CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_set_visual(sph_t* s, int enable)
+{
+    if (!s) return SPH_ERR_ARG;
+    CU_TRY(s, cudaSetDevice(s->device));
+    if (enable && !s->clr) {
+        CU_TRY(s, cudaMalloc((void**)&s->clr, (size_t)s->nAlloc * sizeof(float4)));
+        CU_TRY(s, cudaMalloc((void**)&s->dye, (size_t)s->nAlloc * sizeof(float)));
+        CU_TRY(s, cudaMemsetAsync(s->clr, 0, (size_t)s->nAlloc * sizeof(float4), s->stream));
+        CU_TRY(s, cudaMemsetAsync(s->dye, 0, (size_t)s->nAlloc * sizeof(float), s->stream));
+    }
+    s->visual = enable != 0;
     return SPH_OK;
 }
 
@@ -604,6 +628,7 @@ extern "C" int sph_slab_force(sph_t* s)
     if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_force: call sph_slab_sort first");
     sph_launch_force(launcher(s), s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
                      s->nlist, s->ncount, s->ctaRows, s->vel, b.first, b.count);
+    if (sph_needs_obstacles(s->par)) sph_launch_obstacles(launcher(s), b.parLocal, s->posP, s->velD, s->vel, b.first, b.count);
     s->stepped = true;
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;

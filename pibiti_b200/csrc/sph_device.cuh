@@ -88,3 +88,11 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
                       const uint32_t* ctaRows, float4* velOut, int first, int count);
+
+// ---- sph_extras_kernels.cu --------------------------------------------------------------------
+bool sph_needs_obstacles(const SimParams& par);        // height map or rotor configured
+void sph_launch_obstacles(const SphLaunch& L, const SimParams& par, const float4* posP, const float4* velD, float4* velNew,
+                          int first, int count);
+void sph_launch_color_dye(const SphLaunch& L, const SimParams& par, const float4* posS, const float4* velS, const float4* velD,
+                          const float4* velNew, const uint32_t* keyS, const uint32_t* cellStart, const uint32_t* idx,
+                          float4* clr, float* dye, int first, int count);

@@ -78,7 +78,7 @@ STAGE_NAMES = ("integrate_hash", "sort", "reorder", "density", "force")
 
 # every symbol include/sph_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
-    "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_step", "sph_sync",
+    "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_set_visual", "sph_step", "sph_sync",
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
     "sph_version",
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     lib.sph_destroy.argtypes = [vp]
     lib.sph_set_params.argtypes = [vp, vp]
     lib.sph_get_params.argtypes = [vp, vp]
+    lib.sph_set_visual.argtypes = [vp, ci]
     lib.sph_step.argtypes = [vp, ci]
     lib.sph_sync.argtypes = [vp]
     lib.sph_set_array.argtypes = [vp, ci, vp, ci, ci]
@@ -184,6 +185,9 @@ class SphSystem:
     def set_params(self, params: np.ndarray):
         self.params = params_array(params.tobytes())
         self._check(self.lib.sph_set_params(self.h, _ptr(self.params)), "sph_set_params")
+
+    def set_visual(self, on: bool = True):
+        self._check(self.lib.sph_set_visual(self.h, int(on)), "sph_set_visual")
 
     def step(self, nsteps: int = 1):
         self._check(self.lib.sph_step(self.h, nsteps), "sph_step")

@@ -53,14 +53,15 @@ def titles(golden):
 
 def test_golden_lists_expected_scenes(golden_steps):
     t = titles(golden_steps)
-    assert "box small default" in t and "Stiff  Dam break" in t and "mini dense cells" in t and len(t) >= 12
+    assert "box small default" in t and "Stiff  Dam break" in t and "mini dense cells" in t and len(t) >= 17
     # the truncation quirk is really exercised by one fixture
     assert int(golden_steps["mini_dense_cells/1/max_cell"]) > 8
 
 
 @pytest.mark.parametrize("title", ["box small default", "Stiff  Dam break", "mini box", "mini dense cells", "mini random",
                                    "mini cylinder Y", "mini cylinder Z", "mini sphere", "mini wrap Z", "mini cycle Z",
-                                   "mini waves", "mini collider accel"])
+                                   "mini waves", "mini collider accel", "mini heightmap XZ", "mini heightmap YZ holes",
+                                   "mini rotor Z", "mini rotor Y", "mini propeller pair"])
 def test_port_reproduces_reference_vectors(oracle_port, golden_steps, title):
     run_against_golden(oracle_port, golden_steps, title)
 
