@@ -147,7 +147,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     sph_pair_default_config(&s->cfg);
     if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1,threads,cap,kMax" -- tuning / test aid
         char mode[8] = {0};  int t = 0, c = 0, k = 0;
-        if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024) {
+        if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024 && k % 4 == 0) {
             s->cfg.mode = strcmp(mode, "tma") == 0 ? SPH_PAIR_TMA : SPH_PAIR_L1;
             s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
         }

@@ -558,7 +558,7 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
     const float h2 = par.h2;
     const long long C = par.numCells;
-    uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;
+    uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;      // [cta][k][thread]: row k is 4 B x T, coalesced
 
     float sum = 0.f;  uint32_t cnt = 0;
     auto span = [&](uint32_t a, uint32_t e) {
@@ -631,11 +631,32 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
     float3 f = make_float3(0.f, 0.f, 0.f);
     if (cnt != kListInvalid) {
         const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+        // list entries are consumed four at a time; the next four are in flight while these are evaluated
         const uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;
-        #pragma unroll 4
-        for (uint32_t t = 0; t < cnt; t++) {
-            const uint32_t g = __ldg(lst + (size_t)t * T);
-            force_pair(__ldg(posP + g), __ldg(velD + g), pi, vi, pp.w, vd.w, k, f);
+        const uint32_t groups = (cnt + 3) >> 2;
+        auto load4 = [&](uint32_t q) {
+            const uint32_t t0 = 4 * q;
+            uint4 e;
+            e.x = t0 < cnt ? __ldg(lst + (size_t)t0 * T) : 0u;
+            e.y = t0 + 1 < cnt ? __ldg(lst + (size_t)(t0 + 1) * T) : 0u;
+            e.z = t0 + 2 < cnt ? __ldg(lst + (size_t)(t0 + 2) * T) : 0u;
+            e.w = t0 + 3 < cnt ? __ldg(lst + (size_t)(t0 + 3) * T) : 0u;
+            return e;
+        };
+        uint4 cur = load4(0);
+        for (uint32_t q = 0; q < groups; q++) {
+            const uint4 nxt = load4(q + 1);
+            const uint32_t left = cnt - 4 * q;              // >= 1
+            const uint32_t g0 = cur.x, g1 = left > 1 ? cur.y : cur.x, g2 = left > 2 ? cur.z : cur.x, g3 = left > 3 ? cur.w : cur.x;
+            const float4 q0 = __ldg(posP + g0), u0 = __ldg(velD + g0);
+            const float4 q1 = __ldg(posP + g1), u1 = __ldg(velD + g1);
+            const float4 q2 = __ldg(posP + g2), u2 = __ldg(velD + g2);
+            const float4 q3 = __ldg(posP + g3), u3 = __ldg(velD + g3);
+            force_pair(q0, u0, pi, vi, pp.w, vd.w, k, f);
+            if (left > 1) force_pair(q1, u1, pi, vi, pp.w, vd.w, k, f);
+            if (left > 2) force_pair(q2, u2, pi, vi, pp.w, vd.w, k, f);
+            if (left > 3) force_pair(q3, u3, pi, vi, pp.w, vd.w, k, f);
+            cur = nxt;
         }
     } else {
         const bool trunc = __ldg(maxCount) > par.maxParInCell;
@@ -653,7 +674,7 @@ inline size_t force_smem(const SphPairConfig& c) { return (size_t)c.cap * 32 + (
 
 void sph_pair_default_config(SphPairConfig* cfg)
 {
-    cfg->mode = SPH_PAIR_L1;  cfg->threads = 128;  cfg->cap = 1344;  cfg->kMax = 48;
+    cfg->mode = SPH_PAIR_L1;  cfg->threads = 128;  cfg->cap = 1344;  cfg->kMax = 48;      // kMax must be a multiple of 4
 }
 
 size_t sph_pair_blocks(const SphPairConfig& cfg, int n) { return ((size_t)n + cfg.threads - 1) / cfg.threads; }
