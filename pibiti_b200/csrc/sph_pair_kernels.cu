@@ -541,6 +541,11 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
 // [cta][k][thread] like the staged variant.  Which variant runs is a launch-time choice
 // (SphPairConfig::mode); profiles/ holds the ncu evidence for the default.
 
+// The candidate loop is branch-free: c = max(h2 - r2, 0) is added unconditionally (c > 0 <=> r2 < h2 because a
+// float subtraction has the exact sign), and a hit's sorted index goes to the thread's column of the CTA's list
+// block [k][thread] with one predicated 4-byte store (row k of a warp = one 128-byte segment).
+// (Measured alternative, profiles/: lists built in shared memory and written with one TMA bulk store need fewer
+// instructions but 25 KB of shared memory per CTA; the lost occupancy costs more than the instructions save.)
 __global__ void __launch_bounds__(256)
 k_density_l1(const __grid_constant__ SimParams par, int kMax,
              const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
@@ -558,20 +563,21 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
     const float h2 = par.h2;
     const long long C = par.numCells;
-    uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;      // [cta][k][thread]: row k is 4 B x T, coalesced
+    uint32_t* lp = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;     // next free entry of this thread's column
+    const uint32_t kmax = (uint32_t)kMax;
 
     float sum = 0.f;  uint32_t cnt = 0;
     auto span = [&](uint32_t a, uint32_t e) {
         #pragma unroll 4
         for (uint32_t g = a; g < e; g++) {
-            float4 q = __ldg(posS + g);
-            float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
-            if (r2 < h2) {
-                float c = h2 - r2;
-                sum += c * c * c;
-                if (cnt < (uint32_t)kMax) lst[(size_t)cnt * T] = g;
-                cnt++;
-            }
+            const float4 q = __ldg(posS + g);
+            const float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
+            const float c = fmaxf(__fsub_rn(h2, r2), 0.f);
+            sum = fmaf(c * c, c, sum);
+            const bool hit = c > 0.f;
+            if (hit && cnt < kmax) *lp = g;
+            lp += hit ? T : 0;
+            cnt += hit ? 1u : 0u;
         }
     };
     auto run = [&](uint32_t a, uint32_t e) {
@@ -604,7 +610,7 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float pres = (dens - par.restDensity) * par.stiffness;
     posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
     velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
-    ncount[i] = cnt <= (uint32_t)kMax ? (uint16_t)cnt : (uint16_t)kListInvalid;
+    ncount[i] = cnt <= kmax ? (uint16_t)cnt : (uint16_t)kListInvalid;
     if (neighborCounts) neighborCounts[i] = cnt;
 }
 
