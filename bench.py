@@ -223,8 +223,7 @@ def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) ->
     from oracle import oracle as orc                  # the one place bench.py executes oracle/
     from pibiti_b200 import host
     O = orc.load(None)
-    if threads:
-        O.set_threads(threads)
+    O.set_threads(threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     s = host.CSph(device=-1)
     s.select_scene(title)
     if "drop" in title:
@@ -254,6 +253,8 @@ def run_reference(args) -> dict:
     from oracle import oracle as orc
     from pibiti_b200 import host
     O = orc.load(None)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would serialise the baseline)
+    O.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     s = host.CSph(device=-1)
     s.select_scene(sample_title)
     if "drop" in title:

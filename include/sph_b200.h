@@ -146,6 +146,8 @@ int sph_slab_pack_dp(sph_t* s, float* d_down, float* d_up, int capRows, int* cou
 int sph_slab_ghost_counts(sph_t* s, int* counts2 /* rows expected from below, from above */);
 int sph_slab_unpack_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove);
 int sph_slab_force(sph_t* s);
+/* diagnostics after a step: {largest real cell, work-set size, ghosts below, owned, ghosts above, retired slots} */
+int sph_slab_stats(sph_t* s, int* out6);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@ struct sph_system {
 
     bool timing = false;
     cudaEvent_t ev[SPH_STAGE_COUNT + 1] = {};
+    cudaEvent_t evForce[2] = {};            // slab mode: the force phase does not start where the density phase ends
     float stageMs[SPH_STAGE_COUNT] = {};
 
     std::string err;
@@ -102,6 +103,7 @@ extern "C" int sph_destroy(sph_t* s)
     for (void* b : bufs) if (b) cudaFree(b);
     if (s->hostInts) cudaFreeHost(s->hostInts);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s->evForce) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return SPH_OK;
@@ -165,6 +167,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     CU_TRY(nullptr, cudaMallocHost((void**)&s->hostInts, 64));
     CU_TRY(nullptr, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& ev : s->ev) CU_TRY(nullptr, cudaEventCreate(&ev));
+    for (auto& ev : s->evForce) CU_TRY(nullptr, cudaEventCreate(&ev));
 
     CU_TRY(nullptr, sph_pair_prepare(s->cfg));
 
@@ -397,7 +400,12 @@ extern "C" int sph_get_timings(sph_t* s, float* msPerStage, int enable)
         CU_TRY(s, cudaStreamSynchronize(s->stream));
         for (int k = 0; k < SPH_STAGE_COUNT; k++) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+            cudaEvent_t a = s->ev[k], b = s->ev[k + 1];
+            if (s->slab.on) {                       // slab mode records the two pair kernels only
+                if (k == SPH_STAGE_FORCE) { a = s->evForce[0];  b = s->evForce[1]; }
+                else if (k != SPH_STAGE_DENSITY) { msPerStage[k] = -1.f;  continue; }
+            }
+            if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
             msPerStage[k] = ms;
         }
     } else if (msPerStage) {
@@ -555,7 +563,8 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
     CU_TRY(s, cudaMemcpyAsync(s->hostInts + 5, s->counters + kDevWork, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     if (s->hostInts[6])
-        return fail(s, SPH_ERR_ARG, "slab exchange overflow: a message section or the particle capacity (%d) was too small", s->nAlloc);
+        return fail(s, SPH_ERR_ARG, "slab exchange overflow: a message section was too small (raise SlabCaps) or the work set "
+                    "(%u of capacity %d) does not fit", s->hostInts[5], s->nAlloc);
     b.g0 = (int)s->hostInts[0];  b.g1 = (int)s->hostInts[1];  b.g2 = (int)s->hostInts[2];
     b.bLoEnd = (int)s->hostInts[3];  b.bHiStart = (int)s->hostInts[4];
     s->cur = outb;
@@ -570,8 +579,10 @@ extern "C" int sph_slab_density(sph_t* s)
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
     if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_density: call sph_slab_sort first");
+    if (s->timing) cudaEventRecord(s->ev[3], s->stream);
     sph_launch_density(launcher(s), s->cfg, b.parLocal, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount,
                        s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, b.first, b.count);
+    if (s->timing) cudaEventRecord(s->ev[4], s->stream);
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
 }
@@ -593,6 +604,18 @@ extern "C" int sph_slab_pack_dp(sph_t* s, float* d_down, float* d_up, int capRow
         CU_TRY(s, cudaMemcpyAsync(d_up + 4 * (size_t)nUp, s->velD + b.bHiStart, (size_t)nUp * 16, cudaMemcpyDeviceToDevice, s->stream));
     }
     counts2[0] = nDown;  counts2[1] = nUp;
+    return SPH_OK;
+}
+
+// diagnostics: {largest real cell, work-set size, ghosts below, owned, ghosts above, retired slots}
+extern "C" int sph_slab_stats(sph_t* s, int* out6)
+{
+    SLAB_CHECK(s);
+    CU_TRY(s, cudaMemcpyAsync(s->hostInts + 8, s->maxCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    const sph_system::Slab& b = s->slab;
+    out6[0] = (int)s->hostInts[8];  out6[1] = b.work;  out6[2] = b.g0;  out6[3] = b.g1 - b.g0;  out6[4] = b.g2 - b.g1;
+    out6[5] = b.work - b.g2;
     return SPH_OK;
 }
 
@@ -626,9 +649,11 @@ extern "C" int sph_slab_force(sph_t* s)
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
     if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_force: call sph_slab_sort first");
+    if (s->timing) cudaEventRecord(s->evForce[0], s->stream);
     sph_launch_force(launcher(s), s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
                      s->nlist, s->ncount, s->ctaRows, s->vel, b.first, b.count);
     if (sph_needs_obstacles(s->par)) sph_launch_obstacles(launcher(s), b.parLocal, s->posP, s->velD, s->vel, b.first, b.count);
+    if (s->timing) cudaEventRecord(s->evForce[1], s->stream);
     s->stepped = true;
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;

@@ -89,7 +89,7 @@ class SlabCaps:
         return 1 + self.leavers + self.boundary
 
     @staticmethod
-    def for_state(par, pos, cuts, safety: float = 3.0, floor: int = 4096) -> "SlabCaps":
+    def for_state(par, pos, cuts, safety: float = 4.0, floor: int = 16384) -> "SlabCaps":
         """Sized from the initial state: `safety` x the fullest z layer (every rank computes the same numbers)."""
         zc = z_cells(pos, par)
         gz = int(par["gridSize"][0][2])
@@ -201,6 +201,11 @@ class GpuSlabBackend:
     def sync(self):
         self.sys.sync()
 
+    def stats(self) -> dict:
+        c = (C.c_int * 6)()
+        self._check(self.L.sph_slab_stats(self.h, c), "sph_slab_stats")
+        return dict(zip(("max_cell", "work", "ghosts_below", "owned", "ghosts_above", "retired"), list(c)))
+
     def empty_message(self):
         return self.torch.zeros((self.caps.rows, REC), dtype=self.torch.float32, device=self.device)
 
@@ -276,6 +281,14 @@ class DistComm:
         if as_numpy:
             return [(below.numpy(), above.numpy())]
         return [(below, above)]
+
+
+def _gather_profile(dist, prof, steps, world, extra=None):
+    mine = {k: round(v * 1e3 / steps, 3) for k, v in prof.items()}
+    mine.update(extra or {})
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    return out
 
 
 def _copy(x):
@@ -381,6 +394,8 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     stream = be.stream
 
     prof = {} if os.environ.get("SPH_SLAB_PROFILE") else None
+    if prof is not None:
+        be.sys.enable_timings(True)
 
     def one_step():
         s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
@@ -456,7 +471,10 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
                 "steps": e2e_steps, "api": "per rank: owned records pinned host -> device, slab step, device -> pinned host"},
         "gpu_launches": int(launches),
         "halo_bytes_per_step_rank0": comm.bytes_sent // max(args.steps + warm + e2e_steps, 1),
-        "phase_ms_rank0": {k: round(v * 1e3 / (args.steps + warm + e2e_steps), 3) for k, v in prof.items()} if prof else None,
+        "phase_ms_by_rank": _gather_profile(dist, prof, args.steps + warm + e2e_steps, world,
+                                             {"kernel_ms_last_step": {k: round(v, 3) for k, v in be.sys.timings().items() if v >= 0},
+                                              "stats": be.stats()})
+        if prof is not None else None,
         "roofline": None,
     }
     return out
