@@ -31,6 +31,13 @@ struct sph_system {
     SphPairConfig cfg;
     long long launches = 0;
 
+    // CUDA-graph replay of a step (see replay_step_graph)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned long long version = 0; int kernels = 0; };
+    StepGraph graph[2];
+    unsigned long long stateVersion = 1;    // bumped by anything that changes what a step launches
+    int stepsSinceChange = 0;
+    bool useGraphs = true;
+
     // slab mode (sph_slab_*): owned z layers [zLo,zHi), one ghost layer towards each existing neighbour
     struct Slab {
         bool on = false;
@@ -101,6 +108,7 @@ extern "C" int sph_destroy(sph_t* s)
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
                     s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->clr, s->dye};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->hostInts) cudaFreeHost(s->hostInts);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->evForce) if (e) cudaEventDestroy(e);
@@ -170,6 +178,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     for (auto& ev : s->evForce) CU_TRY(nullptr, cudaEventCreate(&ev));
 
     CU_TRY(nullptr, sph_pair_prepare(s->cfg));
+    if (const char* env = getenv("SPH_B200_GRAPHS")) s->useGraphs = atoi(env) != 0;
 
     CU_TRY(nullptr, cudaMemsetAsync(s->pos[0], 0, n * sizeof(float4), s->stream));
     CU_TRY(nullptr, cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
@@ -188,6 +197,7 @@ extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
     if ((int)p->numParticles > s->nAlloc || (int)p->numCells > s->cellsAlloc)
         return fail(s, SPH_ERR_PARAMS, "sph_set_params: numParticles/numCells exceed the allocation of sph_create");
     if (p->numCells != s->par.numCells || p->numParticles != s->par.numParticles) s->stepped = false;
+    if (memcmp(&s->par, p, sizeof(SimParams)) != 0) { s->stateVersion++;  s->stepsSinceChange = 0; }
     s->par = *p;
     if (s->slab.on) {
         s->slab.parLocal = *p;
@@ -203,37 +213,74 @@ extern "C" int sph_get_params(sph_t* s, struct SimParams* out)
     return SPH_OK;
 }
 
+// the kernel sequence of one step, reading slot buffers `in` and writing `in^1`
+static void enqueue_step(sph_system* s, int in, bool tm)
+{
+    const int n = (int)s->par.numParticles, C = (int)s->par.numCells, outb = in ^ 1;
+    SphLaunch L = launcher(s);
+    if (tm) cudaEventRecord(s->ev[0], s->stream);
+    sph_launch_integrate_hash(L, s->par, s->pos[in], s->vel, s->keyU, s->rankU, s->cellCount, 0, n);
+    if (tm) cudaEventRecord(s->ev[1], s->stream);
+    sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, C, C);
+    sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, n);
+    if (tm) cudaEventRecord(s->ev[2], s->stream);
+    sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel,
+                           s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
+    if (tm) cudaEventRecord(s->ev[3], s->stream);
+    sph_launch_density(L, s->cfg, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
+                       s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, n);
+    if (tm) cudaEventRecord(s->ev[4], s->stream);
+    sph_launch_force(L, s->cfg, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
+                     s->nlist, s->ncount, s->ctaRows, s->vel, 0, n);
+    if (sph_needs_obstacles(s->par)) sph_launch_obstacles(L, s->par, s->posP, s->velD, s->vel, 0, n);
+    if (s->visual)
+        sph_launch_color_dye(L, s->par, s->pos[outb], s->velS, s->velD, s->vel, s->keyS, s->cellStart, s->idx[outb],
+                             s->clr, s->dye, 0, n);
+    if (tm) cudaEventRecord(s->ev[5], s->stream);
+}
+
+// A step whose parameters did not change since the previous one is replayed as a CUDA graph (one per ping-pong
+// parity): a launch-bound small scene (the default 57K-particle scene is ~60 us of kernels) then pays one graph
+// launch instead of eight kernel launches.  Parameters are kernel arguments, so a change invalidates the graphs.
+static bool replay_step_graph(sph_system* s, int in)
+{
+    sph_system::StepGraph& g = s->graph[in];
+    if (g.exec && g.version != s->stateVersion) {
+        cudaGraphExecDestroy(g.exec);  g.exec = nullptr;
+    }
+    if (!g.exec) {
+        const long long before = s->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+        enqueue_step(s, in, false);
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        g.kernels = (int)(s->launches - before);
+        s->launches = before;
+        if (e != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError();  g.exec = nullptr;  return false; }
+        g.version = s->stateVersion;
+    }
+    if (cudaGraphLaunch(g.exec, s->stream) != cudaSuccess) { cudaGetLastError(); return false; }
+    s->launches += g.kernels;
+    return true;
+}
+
 extern "C" int sph_step(sph_t* s, int nsteps)
 {
     if (!s || nsteps < 0) return SPH_ERR_ARG;
     if (s->slab.on) return fail(s, SPH_ERR_STATE, "sph_step: handle is in slab mode; drive it with the sph_slab_* phases");
     CU_TRY(s, cudaSetDevice(s->device));
-    const int n = (int)s->par.numParticles, C = (int)s->par.numCells;
-    SphLaunch L = launcher(s);
     for (int it = 0; it < nsteps; it++) {
         const bool tm = s->timing && it == nsteps - 1;
-        const int in = s->cur, outb = s->cur ^ 1;
-        if (tm) cudaEventRecord(s->ev[0], s->stream);
-        sph_launch_integrate_hash(L, s->par, s->pos[in], s->vel, s->keyU, s->rankU, s->cellCount, 0, n);
-        if (tm) cudaEventRecord(s->ev[1], s->stream);
-        sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, C, C);
-        sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, n);
-        if (tm) cudaEventRecord(s->ev[2], s->stream);
-        sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel,
-                               s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
-        if (tm) cudaEventRecord(s->ev[3], s->stream);
-        sph_launch_density(L, s->cfg, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
-                           s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, n);
-        if (tm) cudaEventRecord(s->ev[4], s->stream);
-        sph_launch_force(L, s->cfg, s->par, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
-                         s->nlist, s->ncount, s->ctaRows, s->vel, 0, n);
-        if (sph_needs_obstacles(s->par)) sph_launch_obstacles(L, s->par, s->posP, s->velD, s->vel, 0, n);
-        if (s->visual)
-            sph_launch_color_dye(L, s->par, s->pos[outb], s->velS, s->velD, s->vel, s->keyS, s->cellStart, s->idx[outb],
-                                 s->clr, s->dye, 0, n);
-        if (tm) cudaEventRecord(s->ev[5], s->stream);
-        s->cur = outb;
+        // graphs only once the parameters have been stable for two steps (a scene whose host prologue edits them
+        // every step -- wave phase, rotor angle -- would re-capture each time)
+        const bool useGraph = s->useGraphs && !s->timing && s->stepsSinceChange >= 2;
+        if (!(useGraph && replay_step_graph(s, s->cur))) enqueue_step(s, s->cur, tm);
+        s->cur ^= 1;
         s->stepped = true;
+        if (s->stepsSinceChange < 1000) s->stepsSinceChange++;
     }
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
@@ -319,6 +366,7 @@ extern "C" int sph_set_visual(sph_t* s, int enable)
         CU_TRY(s, cudaMemsetAsync(s->dye, 0, (size_t)s->nAlloc * sizeof(float), s->stream));
     }
     s->visual = enable != 0;
+    s->stateVersion++;
     return SPH_OK;
 }
 

@@ -167,6 +167,25 @@ __device__ __forceinline__ long long row_hash(const SimParams& par, uint32_t key
     return (long long)key + (long long)dz * par.gridSize_yx + (long long)dy * par.gridSize.x;
 }
 
+// Truncating mode (some cell holds more than maxParInCell particles): the three cells of a row are
+// still walked as ONE run unless one of them overflows; only then each cell is cut to its first maxParInCell entries.
+// b[0..ncell] = cellStart of the (clipped) cells hb-1..hb+1 and one past; returns ncell (0: nothing to walk).
+__device__ __forceinline__ int row_cells(const uint32_t* __restrict__ cellStart, long long hb, long long C, uint32_t maxPar,
+                                         uint32_t b[4], bool& overflow)
+{
+    long long c0 = hb - 1, c1 = hb + 1;
+    if (c0 < 0) c0 = 0;
+    if (c1 > C - 1) c1 = C - 1;
+    if (c0 > c1) return 0;
+    const int ncell = (int)(c1 - c0) + 1;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) b[k] = (k <= ncell) ? __ldg(cellStart + c0 + k) : 0u;
+    overflow = false;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) if (k < ncell && b[k + 1] - b[k] > maxPar) overflow = true;
+    return ncell;
+}
+
 // ---- density -------------------------------------------------------------------------------------
 
 // r2 exactly as the CPU evaluates "p.x*p.x + p.y*p.y + p.z*p.z" (no contraction)
@@ -251,13 +270,13 @@ __device__ __forceinline__ void density_particle(const StageTable& st, const flo
                 if (sg < 0) continue;
                 cand = sbuf;  shift = (int)st.segS0[sg] - (int)st.segG0[sg];
             }
-            for (int x = -1; x <= 1; x++) {
-                long long h = hb + x;
-                if (h < 0 || h >= C) continue;
-                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
-                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
-                density_run<STAGED>(cand, shift, a, e, i, pi, h2, sum, cnt, lc);
-            }
+            uint32_t b[4];  bool over;
+            const int ncell = row_cells(cellStart, hb, C, par.maxParInCell, b, over);
+            if (ncell == 0) continue;
+            if (!over) { density_run<STAGED>(cand, shift, b[0], b[ncell], i, pi, h2, sum, cnt, lc);  continue; }
+            #pragma unroll
+            for (int x = 0; x < 3; x++)
+                if (x < ncell) density_run<STAGED>(cand, shift, b[x], min(b[x + 1], b[x] + par.maxParInCell), i, pi, h2, sum, cnt, lc);
         }
     }
 }
@@ -407,13 +426,13 @@ __device__ __forceinline__ float3 force_particle_walk(const StageTable& st, cons
             if (!run_bounds(cellStart, hb, C, a, e)) continue;
             force_run(c0, c1, shift, a, e, i, pi, vi, pp.w, vd.w, k, f);
         } else {
-            for (int x = -1; x <= 1; x++) {
-                long long h = hb + x;
-                if (h < 0 || h >= C) continue;
-                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
-                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
-                force_run(c0, c1, shift, a, e, i, pi, vi, pp.w, vd.w, k, f);
-            }
+            uint32_t b[4];  bool over;
+            const int ncell = row_cells(cellStart, hb, C, par.maxParInCell, b, over);
+            if (ncell == 0) continue;
+            if (!over) { force_run(c0, c1, shift, b[0], b[ncell], i, pi, vi, pp.w, vd.w, k, f);  continue; }
+            #pragma unroll
+            for (int x = 0; x < 3; x++)
+                if (x < ncell) force_run(c0, c1, shift, b[x], min(b[x + 1], b[x] + par.maxParInCell), i, pi, vi, pp.w, vd.w, k, f);
         }
     }
     return f;
@@ -596,14 +615,13 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     } else {
         #pragma unroll 1
         for (int r = 0; r < kRows; r++) {
-            const long long hb = row_hash(par, key, r);
-            for (int x = -1; x <= 1; x++) {
-                long long h = hb + x;
-                if (h < 0 || h >= C) continue;
-                uint32_t a = __ldg(cellStart + h), e = __ldg(cellStart + h + 1);
-                if (e - a > par.maxParInCell) e = a + par.maxParInCell;
-                run(a, e);
-            }
+            uint32_t b[4];  bool over;
+            const int ncell = row_cells(cellStart, row_hash(par, key, r), C, par.maxParInCell, b, over);
+            if (ncell == 0) continue;
+            if (!over) { run(b[0], b[ncell]);  continue; }
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (k < ncell) run(b[k], min(b[k + 1], b[k] + par.maxParInCell));
         }
     }
     const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
