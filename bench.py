@@ -186,10 +186,15 @@ def run_ours_single(args) -> dict:
     assert np.isfinite(hvel.numpy()).all(), "non-finite velocities after the benchmark"
 
     hbm, hbm_src = measured_peaks()
-    force_s = stage_ms["force"] * 1e-3
-    achieved = STAGE_BYTES["force"] * n / force_s / 1e9
+    # the dominant kernel is whichever pair kernel took longer in this run (density since the force kernel
+    # consumes neighbour lists)
+    dom = "density" if stage_ms["density"] >= stage_ms["force"] else "force"
+    dom_kernel = {"density": "k_density_l1 (density/pressure + neighbour-list build)",
+                  "force": "k_force_l1 (pair force over neighbour lists)"}[dom]
+    achieved = STAGE_BYTES[dom] * n / (stage_ms[dom] * 1e-3) / 1e9
     stages = {k: {"ms": round(stage_ms[k], 4), "algorithmic_GBps": round(STAGE_BYTES[k] * n / (stage_ms[k] * 1e-3) / 1e9, 1),
-                  "hbm_frac": round(STAGE_BYTES[k] * n / (stage_ms[k] * 1e-3) / 1e9 / hbm, 4)} for k in stage_ms}
+                  "hbm_frac": round(STAGE_BYTES[k] * n / (stage_ms[k] * 1e-3) / 1e9 / hbm, 4),
+                  "dram_traffic_bytes_ncu": TRAFFIC_BYTES.get(k)} for k in stage_ms}
     pair_s = (stage_ms["density"] + stage_ms["force"]) * 1e-3
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -202,9 +207,9 @@ def run_ours_single(args) -> dict:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
                 "steps": e2e_steps, "api": "cSPH setArray(pos,vel) -> Update -> getArray(pos,vel), pinned host buffers"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_force_l1 (pair force over neighbour lists)", "achieved": round(achieved, 1), "peak": hbm,
-                     "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": TRAFFIC_BYTES.get("force"),
-                     "peak_source": hbm_src, "algorithmic_bytes_per_particle": STAGE_BYTES["force"],
+        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 1), "peak": hbm,
+                     "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": TRAFFIC_BYTES.get(dom),
+                     "peak_source": hbm_src, "algorithmic_bytes_per_particle": STAGE_BYTES[dom],
                      "note": "density+force are FP32/shared-memory bound, not HBM bound (SURVEY.md D7); see fp32_frac",
                      "fp32_frac_density_force": round(PAIR_FLOP_PER_PARTICLE * n / pair_s / 1e12 / FP32_PEAK_TFLOPS, 4),
                      "stages": stages},
@@ -213,9 +218,9 @@ def run_ours_single(args) -> dict:
 
 
 # measured with `ncu --set full` on "tank 8M drop" (profiles/r01_*_l1.txt): dram__bytes_read.sum + dram__bytes_write.sum
-# per launch.  The force kernel's traffic is ~3x its algorithmic bytes because it also streams the neighbour lists
-# (8.4M x ~27 x 4 B = 0.9 GB) that save it two thirds of its instructions.
-TRAFFIC_BYTES: dict = {"force": 1_386_462_600, "density": 1_558_815_560}
+# per launch.  Both pair kernels move ~3x their algorithmic bytes because of the neighbour lists (8.4M x ~27 x 4 B =
+# 0.9 GB written by density, read by force) -- the price of a force kernel with a third of the instructions.
+TRAFFIC_BYTES: dict = {"force": 1_373_744_288, "density": 1_544_683_688}
 
 
 def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> dict:

@@ -582,21 +582,22 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
     const float h2 = par.h2;
     const long long C = par.numCells;
-    uint32_t* lp = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;     // next free entry of this thread's column
-    const uint32_t kmax = (uint32_t)kMax;
+    // this thread's column of the CTA's list block [k][thread]: element offset `off` advances one row per hit
+    uint32_t* const lb = nlist + (size_t)blockIdx.x * kMax * T;
+    const uint32_t endOff = (uint32_t)kMax * T;
+    uint32_t off = threadIdx.x;
 
-    float sum = 0.f;  uint32_t cnt = 0;
+    float sum = 0.f;
     auto span = [&](uint32_t a, uint32_t e) {
         #pragma unroll 4
         for (uint32_t g = a; g < e; g++) {
             const float4 q = __ldg(posS + g);
             const float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
-            const float c = fmaxf(__fsub_rn(h2, r2), 0.f);
-            sum = fmaf(c * c, c, sum);
-            const bool hit = c > 0.f;
-            if (hit && cnt < kmax) *lp = g;
-            lp += hit ? T : 0;
-            cnt += hit ? 1u : 0u;
+            const bool hit = r2 < h2;
+            const float c = __fsub_rn(h2, r2);
+            sum += hit ? c * c * c : 0.f;
+            if (hit && off < endOff) lb[off] = g;
+            off += hit ? (uint32_t)T : 0u;
         }
     };
     auto run = [&](uint32_t a, uint32_t e) {
@@ -628,7 +629,8 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float pres = (dens - par.restDensity) * par.stiffness;
     posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
     velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
-    ncount[i] = cnt <= kmax ? (uint16_t)cnt : (uint16_t)kListInvalid;
+    const uint32_t cnt = (off - threadIdx.x) / (uint32_t)T;
+    ncount[i] = cnt <= (uint32_t)kMax ? (uint16_t)cnt : (uint16_t)kListInvalid;
     if (neighborCounts) neighborCounts[i] = cnt;
 }
 
