@@ -120,6 +120,11 @@ public:
     void setArray(bool pos, const float4* data, int start, int count);
     const float4* getPosBuffer() const;         // device pointer (sorted order); reference returns a GL VBO id
 
+    // Checkpoint / resume (the reference has none): parameters, positions and velocities in
+    // original particle order, and the ring / rain / time counters.  0 on success.
+    int SaveState(const char* path);
+    int LoadState(const char* path);
+
     sph_t* solver() const { return sys; }
     const char* lastError() const { return err.c_str(); }
 

@@ -53,6 +53,8 @@ void sphh_mark_changed(sphh_t* h);                                  /* ParamBase
 int  sphh_get_array(sphh_t* h, int velocities, float* out);
 void sphh_set_array(sphh_t* h, int velocities, const float* data, int start, int count);
 sph_t* sphh_solver(sphh_t* h);
+int  sphh_save_state(sphh_t* h, const char* path);                  /* checkpoint: params, pos, vel, ring counters */
+int  sphh_load_state(sphh_t* h, const char* path);
 void sphh_load_options(const char* scenesXmlPath, int* out7);
 
 #ifdef __cplusplus

@@ -101,6 +101,8 @@ void sphh_set_array(sphh_t* h, int velocities, const float* data, int start, int
     S(h)->setArray(velocities != 0, (const float4*)data, start, count);
 }
 sph_t* sphh_solver(sphh_t* h) { return S(h)->solver(); }
+int sphh_save_state(sphh_t* h, const char* path) { return S(h)->SaveState(path); }
+int sphh_load_state(sphh_t* h, const char* path) { return S(h)->LoadState(path); }
 
 void sphh_load_options(const char* scenesXmlPath, int* out7)
 {

@@ -343,6 +343,62 @@ const float4* cSPH::getPosBuffer() const
     return (const float4*)d;
 }
 
+// ---- checkpoint --------------------------------------------------------------------------------
+
+namespace {
+struct CheckpointHeader {
+    char magic[8];              // "SPHB200\0"
+    unsigned version, numParticles;
+    int emitId, cntRain;
+    float fSimTime;
+    int curScene;
+};
+}
+
+int cSPH::SaveState(const char* path)
+{
+    if (!bInitialized) return SPH_ERR_STATE;
+    const float4* pos = getArray(false);
+    const float4* vel = getArray(true);
+    FILE* f = fopen(path, "wb");
+    if (!f) { err = std::string("cannot write ") + path;  return SPH_ERR_ARG; }
+    CheckpointHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "SPHB200", 8);
+    h.version = 1;  h.numParticles = scn.params.numParticles;
+    h.emitId = app.emitId;  h.cntRain = app.cntRain;  h.fSimTime = app.fSimTime;  h.curScene = curScene;
+    const size_t n = scn.params.numParticles;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&scn, sizeof(Scene), 1, f) == 1 &&
+              fwrite(pos, sizeof(float4), n, f) == n && fwrite(vel, sizeof(float4), n, f) == n;
+    fclose(f);
+    if (!ok) { err = std::string("short write to ") + path;  return SPH_ERR_ARG; }
+    return SPH_OK;
+}
+
+int cSPH::LoadState(const char* path)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot read ") + path;  return SPH_ERR_ARG; }
+    CheckpointHeader h;
+    Scene saved;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SPHB200", 8) != 0 || h.version != 1 ||
+        fread(&saved, sizeof(Scene), 1, f) != 1 || saved.params.numParticles != h.numParticles) {
+        fclose(f);  err = std::string("not a checkpoint: ") + path;  return SPH_ERR_ARG;
+    }
+    scn = saved;
+    _FreeMem();  _InitMem();                                // buffers for the saved particle / cell counts
+    const size_t n = h.numParticles;
+    bool ok = fread(hPos, sizeof(float4), n, f) == n && fread(hVel, sizeof(float4), n, f) == n;
+    fclose(f);
+    if (!ok) { err = std::string("truncated checkpoint: ") + path;  return SPH_ERR_ARG; }
+    setArray(0, hPos, 0, (int)n);
+    setArray(1, hVel, 0, (int)n);
+    app.emitId = h.emitId;  app.cntRain = h.cntRain;  app.fSimTime = h.fSimTime;
+    if (h.curScene >= 0 && h.curScene < (int)scenes.size()) curScene = h.curScene;
+    app.bChangedAny = false;                                // _InitMem uploaded scn.params
+    return sys || device < 0 ? SPH_OK : SPH_ERR_CUDA;
+}
+
 // ---- scenes ------------------------------------------------------------------------------------
 
 void cSPH::InitScene()

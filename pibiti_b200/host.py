@@ -23,6 +23,7 @@ HOST_ABI_SYMBOLS = (
     "sphh_select_scene", "sphh_add_scene_xml", "sphh_next_scene", "sphh_prev_scene", "sphh_host_arrays",
     "sphh_reset", "sphh_drop", "sphh_emit_id", "sphh_srand", "sphh_update_emitter", "sphh_update",
     "sphh_mark_changed", "sphh_get_array", "sphh_set_array", "sphh_solver", "sphh_load_options",
+    "sphh_save_state", "sphh_load_state",
 )
 
 EXTRA_FIELDS = ("initMin", "initMax", "initType", "initLast", "spacing", "fCellSize", "dropR", "rain", "rVel", "r2Vel",
@@ -62,6 +63,8 @@ def _bind():
     L.sphh_set_array.argtypes = [vp, ci, vp, ci, ci]
     L.sphh_solver.restype = vp;            L.sphh_solver.argtypes = [vp]
     L.sphh_load_options.argtypes = [cs, vp]
+    L.sphh_save_state.argtypes = [vp, cs]
+    L.sphh_load_state.argtypes = [vp, cs]
     _bound = True
     return L
 
@@ -224,6 +227,15 @@ class CSph:
     def setArray(self, pos: bool, data: np.ndarray, start: int = 0):
         data = np.ascontiguousarray(data, np.float32).reshape(-1, 4)
         self.L.sphh_set_array(self.h, int(pos), _p(data), start, data.shape[0])
+
+    def SaveState(self, path):
+        if self.L.sphh_save_state(self.h, str(path).encode()) != 0:
+            raise SphError("SaveState: " + self.last_error())
+
+    def LoadState(self, path):
+        if self.L.sphh_load_state(self.h, str(path).encode()) != 0:
+            raise SphError("LoadState: " + self.last_error())
+        self._check_solver()
 
     def solver(self) -> _SolverView:
         h = self.L.sphh_solver(self.h)

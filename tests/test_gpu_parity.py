@@ -10,11 +10,12 @@ Bars:
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import pytest
 
-from conftest import sha
+from conftest import ROOT, sha
 from pibiti_b200 import host, lib
 
 pytestmark = pytest.mark.gpu
@@ -383,3 +384,46 @@ def test_eight_million_particles_properties():
     assert np.array_equal(counts[sample], sampled_neighbor_counts(pairs, cs, ce, spos, par, sample))
     vel = g.get_array(lib.SPH_VEL)
     assert np.isfinite(vel).all()
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """Save after 5 steps, run 5 more; a fresh system resumed from the file must arrive at the same bits."""
+    s = host.CSph(device=0)
+    s.select_scene("mini waves")
+    for _ in range(5):
+        s.UpdateEmitter()
+        s.Update()
+    s.SaveState(tmp_path / "ck.bin")
+    for _ in range(5):
+        s.UpdateEmitter()
+        s.Update()
+    a = (s.getArray(False), s.getArray(True))
+    t = host.CSph(device=0)
+    t.LoadState(tmp_path / "ck.bin")
+    for _ in range(5):
+        t.UpdateEmitter()
+        t.Update()
+    assert np.array_equal(t.getArray(False), a[0]) and np.array_equal(t.getArray(True), a[1])
+
+
+@pytest.mark.parametrize("lam,ratio,max_par", [(1, 1.0, 16), (3, 1.25, 16), (8, 1.5, 16), (16, 1.25, 16), (16, 1.0, 64)])
+def test_uniform_random_boxes(oracle_any, lam, ratio, max_par):
+    """BASELINE config 4: uniform random boxes (documented PCG64 seed) at several occupancies, h/cell ratios and
+    maxParInCell: sorted pairs, cell table and neighbour counts bit-exact, density within 1e-5.  lambda = 16 with
+    maxParInCell = 16 exercises the truncating walk on about half of the cells."""
+    sys.path.insert(0, str(ROOT))
+    import bench_sweep
+    n = 32768
+    g, par, pos, vel = bench_sweep.build_system(n, lam, ratio, max_par)
+    o = oracle_any.system(par)
+    o.set_array(0, pos)
+    o.set_array(1, vel)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    dg, do = g.dump(lib.DUMP_DENSITY), o.dump(5)
+    assert np.all(np.abs(dg - do) <= REL * np.abs(do) + 1e-30)
+    if lam == 16 and max_par == 16:
+        assert int(np.bincount(g.dump(lib.DUMP_SORTED_PAIRS)[:, 0]).max()) > 16
+    g.close()
+    o.close()

@@ -170,3 +170,20 @@ def test_update_emitter_prologue():
     for _ in range(4):
         s.UpdateEmitter()                                       # 5th call: rain counter fires a random Drop
     assert s.emitId > 45 and s.emitId < n
+
+
+def test_checkpoint_roundtrip_host_only(tmp_path):
+    s = host.CSph(device=-1)
+    s.select_scene("mini emitter rain")
+    for _ in range(3):
+        s.UpdateEmitter()
+    pos, vel = s.host_arrays()
+    par, eid = s.params, s.emitId
+    s.SaveState(tmp_path / "state.bin")
+    t = host.CSph(device=-1)
+    t.LoadState(tmp_path / "state.bin")
+    assert t.n == s.n and t.emitId == eid and t.params.tobytes() == par.tobytes()
+    p2, v2 = t.host_arrays()
+    assert np.array_equal(p2, pos) and np.array_equal(v2, vel)
+    with pytest.raises(Exception):
+        t.LoadState(tmp_path / "missing.bin")
