@@ -54,6 +54,7 @@ struct sph_system {
         SimParams parLocal;                 // par with numCells = numCellsLocal, for the neighbour walk
     } slab;
     uint32_t* counters = nullptr;           // device: 4 append counters
+    uint32_t* keyMax = nullptr;             // device: slab scan bound (sph_device.cuh kKeyMaxSlots)
     uint32_t* hostInts = nullptr;           // pinned: read-back of counters / cell-table entries
 
     bool timing = false;
@@ -106,7 +107,7 @@ extern "C" int sph_destroy(sph_t* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
-                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->clr, s->dye};
+                    s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->keyMax, s->clr, s->dye};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->hostInts) cudaFreeHost(s->hostInts);
@@ -168,7 +169,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     ALLOC(s->counts, n);  ALLOC(s->pairT, n);
     { unsigned char* lb = nullptr;  ALLOC(lb, sph_pair_list_bytes(s->cfg, (int)n));  s->nlist = lb; }  ALLOC(s->ncount, n);
     ALLOC(s->ctaRows, sph_pair_blocks(s->cfg, (int)n));
-    ALLOC(s->counters, 16);
+    ALLOC(s->counters, 16);  ALLOC(s->keyMax, kKeyMaxSlots + 8);
     ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
 #undef ALLOC
 
@@ -184,6 +185,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     CU_TRY(nullptr, cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
     CU_TRY(nullptr, cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
     CU_TRY(nullptr, cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
+    CU_TRY(nullptr, cudaMemsetAsync(s->keyMax, 0, (kKeyMaxSlots + 8) * sizeof(uint32_t), s->stream));
     sph_launch_iota(launcher(s), s->idx[0], (int)n);
     CU_TRY(nullptr, cudaStreamSynchronize(s->stream));
     *out = s;
@@ -598,8 +600,10 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
     }
     const int W = b.workBound;
     const uint32_t* nDev = s->counters + kDevWork;
-    sph_launch_slab_hash_hist(L, s->par, s->pos[in], s->idx[in], s->keyU, s->rankU, s->cellCount, W, nDev, b.keyOffset, CL);
-    sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL);
+    // the scan covers the occupied part of the table only: largest live key + two layers (all neighbour lookups)
+    sph_launch_slab_hash_hist(L, s->par, s->pos[in], s->idx[in], s->keyU, s->rankU, s->cellCount, W, nDev, b.keyOffset, CL,
+                              s->keyMax, 2u * (uint32_t)yx);
+    sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL, s->keyMax + kKeyMaxSlots);
     if (W > 0) {
         sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, W, nDev);
         sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W, nDev);
@@ -609,7 +613,15 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
     for (int k = 0; k < 5; k++)
         CU_TRY(s, cudaMemcpyAsync(s->hostInts + k, s->cellStart + cells[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaMemcpyAsync(s->hostInts + 5, s->counters + kDevWork, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->hostInts + 7, s->keyMax + kKeyMaxSlots, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaStreamSynchronize(s->stream));
+    // table entries at or above the scan bound were not written this step: no live key is that large, so they equal
+    // the live total, which is the start of the dummy cell (always scanned)
+    {
+        const int lastTileStart = CL / SPH_SCAN_TILE * SPH_SCAN_TILE;
+        for (int k = 0; k < 5; k++)
+            if (cells[k] >= (int)s->hostInts[7] && cells[k] < lastTileStart) s->hostInts[k] = s->hostInts[2];
+    }
     if (s->hostInts[6])
         return fail(s, SPH_ERR_ARG, "slab exchange overflow: a message section was too small (raise SlabCaps) or the work set "
                     "(%u of capacity %d) does not fit", s->hostInts[5], s->nAlloc);

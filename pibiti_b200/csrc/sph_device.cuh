@@ -23,6 +23,8 @@
 #include "sph_params.h"
 
 #define SPH_SCAN_TILE 4096          // cells per scan block (256 threads x 16)
+// slab mode: per-block maxima of the live keys land in kKeyMaxSlots words; word [kKeyMaxSlots] is the scan bound
+static const int kKeyMaxSlots = 64;
 
 struct SphLaunch {
     cudaStream_t stream;
@@ -33,9 +35,10 @@ struct SphLaunch {
 void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel,
                                uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount /*null: integrate only*/,
                                int first, int count);
-// scan of cells [0,numCells); the largest-cell statistic only looks at cells [0,maxCells)
+// scan of cells [0,numCells); the largest-cell statistic only looks at cells [0,maxCells).  boundCells (device,
+// optional): tiles entirely at or above *boundCells, other than the last one, are known to be empty and are skipped
 void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* blockSums,
-                     uint32_t* maxCount, int numCells, int maxCells);
+                     uint32_t* maxCount, int numCells, int maxCells, const uint32_t* boundCells = nullptr);
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
                        const uint32_t* cellStart, uint2* pairT, int n, const uint32_t* nDev = nullptr);
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
@@ -65,7 +68,7 @@ void sph_launch_slab_export(const SphLaunch& L, const float4* pos, const float4*
 void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first, int count);
 void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
                                uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int nMax, const uint32_t* nDev,
-                               long long keyOffset, int numCellsLocal);
+                               long long keyOffset, int numCellsLocal, uint32_t* keyMaxSlots, uint32_t guardCells);
 void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void* inAbove, const void* ownDown, const void* ownUp,
                             int capL, int capB, float4* pos, float4* vel, uint32_t* idx, int work0, int capacity, uint32_t* dev);
 

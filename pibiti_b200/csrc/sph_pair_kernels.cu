@@ -27,6 +27,8 @@
 //   * force: compForcePair / compForceCell (Kernel_Cell.cui:210-261), then F*mass*dt, sphere
 //     collider, accelerators, newVel = vel + dv (System.cu:247-250,373-402).
 #include "sph_device.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -560,9 +562,9 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
 // [cta][k][thread] like the staged variant.  Which variant runs is a launch-time choice
 // (SphPairConfig::mode); profiles/ holds the ncu evidence for the default.
 
-// The candidate loop is branch-free: c = max(h2 - r2, 0) is added unconditionally (c > 0 <=> r2 < h2 because a
-// float subtraction has the exact sign), and a hit's sorted index goes to the thread's column of the CTA's list
-// block [k][thread] with one predicated 4-byte store (row k of a warp = one 128-byte segment).
+// The candidate loop is branch-free: a hit adds c^3 with one predicated FFMA and its sorted index goes to the thread's
+// column of the CTA's list block [k][thread] with one predicated 4-byte store (row k of a warp = one 128-byte
+// segment).  Left to the compiler the store becomes a branch around five address instructions per candidate.
 // (Measured alternative, profiles/: lists built in shared memory and written with one TMA bulk store need fewer
 // instructions but 25 KB of shared memory per CTA; the lost occupancy costs more than the instructions save.)
 __global__ void __launch_bounds__(256)
@@ -582,10 +584,11 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
     const float h2 = par.h2;
     const long long C = par.numCells;
-    // this thread's column of the CTA's list block [k][thread]: element offset `off` advances one row per hit
-    uint32_t* const lb = nlist + (size_t)blockIdx.x * kMax * T;
-    const uint32_t endOff = (uint32_t)kMax * T;
-    uint32_t off = threadIdx.x;
+    // this thread's column of the CTA's list block [k][thread]: byte offset `off` advances one row per hit
+    char* const lb = reinterpret_cast<char*>(nlist + (size_t)blockIdx.x * kMax * T);
+    const uint32_t rowBytes = (uint32_t)T * 4u;
+    const uint32_t endOff = (uint32_t)kMax * rowBytes;
+    uint32_t off = threadIdx.x * 4u;
 
     float sum = 0.f;
     auto span = [&](uint32_t a, uint32_t e) {
@@ -595,9 +598,12 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
             const float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
             const bool hit = r2 < h2;
             const float c = __fsub_rn(h2, r2);
-            sum += hit ? c * c * c : 0.f;
-            if (hit && off < endOff) lb[off] = g;
-            off += hit ? (uint32_t)T : 0u;
+            sum = hit ? fmaf(c * c, c, sum) : sum;              // one predicated FFMA
+            // the store is predicated, not branched around: the address is formed unconditionally
+            const uint32_t keep = hit && off < endOff;
+            asm volatile("{ .reg .pred p;  setp.ne.u32 p, %2, 0;  @p st.global.u32 [%0], %1; }"
+                         :: "l"(lb + off), "r"(g), "r"(keep));
+            off += hit ? rowBytes : 0u;
         }
     };
     auto run = [&](uint32_t a, uint32_t e) {
@@ -629,11 +635,23 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const float pres = (dens - par.restDensity) * par.stiffness;
     posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
     velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
-    const uint32_t cnt = (off - threadIdx.x) / (uint32_t)T;
+    const uint32_t cnt = (off - threadIdx.x * 4u) / rowBytes;
     ncount[i] = cnt <= (uint32_t)kMax ? (uint16_t)cnt : (uint16_t)kListInvalid;
     if (neighborCounts) neighborCounts[i] = cnt;
 }
 
+// list entries are read once: kStream loads them around L1 (no allocation) so that they do not evict the gathered
+// particle records, which is what the kernel is bound by
+template <bool kStream>
+__device__ __forceinline__ uint32_t load_list_entry(const uint32_t* p)
+{
+    if (!kStream) return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <bool kStream>
 __global__ void __launch_bounds__(256)
 k_force_l1(const __grid_constant__ SimParams par, int kMax,
            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
@@ -663,10 +681,10 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
         auto load4 = [&](uint32_t q) {
             const uint32_t t0 = 4 * q;
             uint4 e;
-            e.x = t0 < cnt ? __ldg(lst + (size_t)t0 * T) : 0u;
-            e.y = t0 + 1 < cnt ? __ldg(lst + (size_t)(t0 + 1) * T) : 0u;
-            e.z = t0 + 2 < cnt ? __ldg(lst + (size_t)(t0 + 2) * T) : 0u;
-            e.w = t0 + 3 < cnt ? __ldg(lst + (size_t)(t0 + 3) * T) : 0u;
+            e.x = t0 < cnt ? load_list_entry<kStream>(lst + (size_t)t0 * T) : 0u;
+            e.y = t0 + 1 < cnt ? load_list_entry<kStream>(lst + (size_t)(t0 + 1) * T) : 0u;
+            e.z = t0 + 2 < cnt ? load_list_entry<kStream>(lst + (size_t)(t0 + 2) * T) : 0u;
+            e.w = t0 + 3 < cnt ? load_list_entry<kStream>(lst + (size_t)(t0 + 3) * T) : 0u;
             return e;
         };
         uint4 cur = load4(0);
@@ -735,6 +753,13 @@ void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimP
     SPH_COUNT(L);
 }
 
+// SPH_B200_FORCE_LISTS=l1|stream (tuning aid): how k_force_l1 reads its neighbour lists
+static bool force_list_streaming()
+{
+    static const int mode = [] { const char* e = getenv("SPH_B200_FORCE_LISTS");  return e && strcmp(e, "l1") == 0 ? 0 : 1; }();
+    return mode != 0;
+}
+
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
@@ -746,8 +771,11 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
     if (cfg.mode == SPH_PAIR_TMA)
         k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
                                                                     (const uint16_t*)nlist, ncount, ctaRows, velOut, first, n);
+    else if (force_list_streaming())
+        k_force_l1<true><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
+                                                               (const uint32_t*)nlist, ncount, velOut, first, n);
     else
-        k_force_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                         (const uint32_t*)nlist, ncount, velOut, first, n);
+        k_force_l1<false><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
+                                                                (const uint32_t*)nlist, ncount, velOut, first, n);
     SPH_COUNT(L);
 }

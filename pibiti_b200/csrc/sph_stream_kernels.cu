@@ -243,10 +243,23 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* to
     return r;
 }
 
+// Occupied-range bound (slab mode).  A slab's cell table spans its whole z range, of which the last slab of a long
+// tank uses a fraction.  The histogram kernel records the largest live key; tiles that lie entirely above
+// bound = largest key + guard (two layers: every neighbour lookup stays below it) hold only zero counts and are not
+// read, zeroed or written.  The last tile (the dummy cell and cellStart[numCells]) is always processed.  cellStart
+// above the bound is stale; nothing on the device reads it and the host substitutes the live total (sph_slab_sort).
+__device__ __forceinline__ bool scan_tile_skipped(const uint32_t* __restrict__ boundCells)
+{
+    if (!boundCells) return false;
+    return (uint32_t)blockIdx.x * SPH_SCAN_TILE >= __ldg(boundCells) && blockIdx.x != gridDim.x - 1;
+}
+
 __global__ void __launch_bounds__(256)
-k_scan_reduce(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tileSums, int numCells)
+k_scan_reduce(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tileSums, int numCells,
+              const uint32_t* __restrict__ boundCells)
 {
     __shared__ uint32_t total;
+    if (scan_tile_skipped(boundCells)) { if (threadIdx.x == 0) tileSums[blockIdx.x] = 0;  return; }
     const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
     uint32_t s = 0;
     if (base + 16 <= numCells) {
@@ -280,9 +293,10 @@ k_scan_tiles(uint32_t* __restrict__ tileSums, int numTiles, uint32_t* __restrict
 
 __global__ void __launch_bounds__(256)
 k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ tileSums,
-             uint32_t* __restrict__ maxCount, int numCells, int maxCells)
+             uint32_t* __restrict__ maxCount, int numCells, int maxCells, const uint32_t* __restrict__ boundCells)
 {
     __shared__ uint32_t total;
+    if (scan_tile_skipped(boundCells)) return;
     const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
     uint32_t c[16];
     uint32_t s = 0, mx = 0;
@@ -555,18 +569,39 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t v, int first, int n)
 __global__ void __launch_bounds__(256)
 k_slab_hash_hist(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const uint32_t* __restrict__ idx,
                  uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU, uint32_t* __restrict__ cellCount,
-                 const uint32_t* __restrict__ nDev, long long keyOffset, int numCellsLocal)
+                 const uint32_t* __restrict__ nDev, long long keyOffset, int numCellsLocal, uint32_t* __restrict__ keyMaxSlots)
 {
+    __shared__ uint32_t blockMax;
+    if (threadIdx.x == 0) blockMax = 0;
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int)*nDev) return;
-    uint32_t key = (uint32_t)numCellsLocal;
-    if (idx[i] != kDeadIndex) {
-        const float4 p = pos[i];
-        long long k = (long long)cell_hash(par, make_float3(p.x, p.y, p.z)) - keyOffset;
-        if (k >= 0 && k < (long long)numCellsLocal) key = (uint32_t)k;
+    uint32_t live1 = 0;                     // live key + 1
+    if (i < (int)*nDev) {
+        uint32_t key = (uint32_t)numCellsLocal;
+        if (idx[i] != kDeadIndex) {
+            const float4 p = pos[i];
+            long long k = (long long)cell_hash(par, make_float3(p.x, p.y, p.z)) - keyOffset;
+            if (k >= 0 && k < (long long)numCellsLocal) { key = (uint32_t)k;  live1 = key + 1; }
+        }
+        keyU[i] = key;
+        rankU[i] = atomicAdd(&cellCount[key], 1u);
     }
-    keyU[i] = key;
-    rankU[i] = atomicAdd(&cellCount[key], 1u);
+    live1 = __reduce_max_sync(0xffffffffu, live1);
+    if ((threadIdx.x & 31) == 0 && live1) atomicMax(&blockMax, live1);
+    __syncthreads();
+    if (threadIdx.x == 0 && blockMax) atomicMax(&keyMaxSlots[blockIdx.x & (kKeyMaxSlots - 1)], blockMax);
+}
+
+// one warp: bound = min(numCellsLocal, largest live key + 1 + guard); the slots are cleared for the next step
+__global__ void k_slab_scan_bound(uint32_t* __restrict__ keyMaxSlots, uint32_t guard, uint32_t numCellsLocal)
+{
+    uint32_t m = 0;
+    for (int k = threadIdx.x; k < kKeyMaxSlots; k += 32) { m = max(m, keyMaxSlots[k]);  keyMaxSlots[k] = 0; }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (threadIdx.x == 0) {
+        unsigned long long b = (unsigned long long)m + guard;
+        keyMaxSlots[kKeyMaxSlots] = b < numCellsLocal ? (uint32_t)b : numCellsLocal;
+    }
 }
 
 inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
@@ -586,12 +621,12 @@ void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4*
 }
 
 void sph_launch_scan(const SphLaunch& L, uint32_t* cellCount, uint32_t* cellStart, uint32_t* tileSums,
-                     uint32_t* maxCount, int numCells, int maxCells)
+                     uint32_t* maxCount, int numCells, int maxCells, const uint32_t* boundCells)
 {
     int tiles = blocks_for(numCells, SPH_SCAN_TILE);
-    k_scan_reduce<<<tiles, 256, 0, L.stream>>>(cellCount, tileSums, numCells);          SPH_COUNT(L);
+    k_scan_reduce<<<tiles, 256, 0, L.stream>>>(cellCount, tileSums, numCells, boundCells);   SPH_COUNT(L);
     k_scan_tiles<<<1, 256, 0, L.stream>>>(tileSums, tiles, maxCount);                   SPH_COUNT(L);
-    k_scan_apply<<<tiles, 256, 0, L.stream>>>(cellCount, cellStart, tileSums, maxCount, numCells, maxCells);  SPH_COUNT(L);
+    k_scan_apply<<<tiles, 256, 0, L.stream>>>(cellCount, cellStart, tileSums, maxCount, numCells, maxCells, boundCells);  SPH_COUNT(L);
 }
 
 void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t* rankU, const uint32_t* idxIn,
@@ -683,10 +718,14 @@ void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first,
 
 void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
                                uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int nMax, const uint32_t* nDev,
-                               long long keyOffset, int numCellsLocal)
+                               long long keyOffset, int numCellsLocal, uint32_t* keyMaxSlots, uint32_t guardCells)
 {
-    if (nMax <= 0) return;
-    k_slab_hash_hist<<<blocks_for(nMax, 256), 256, 0, L.stream>>>(par, pos, idx, keyU, rankU, cellCount, nDev, keyOffset, numCellsLocal);
+    if (nMax > 0) {
+        k_slab_hash_hist<<<blocks_for(nMax, 256), 256, 0, L.stream>>>(par, pos, idx, keyU, rankU, cellCount, nDev, keyOffset,
+                                                                      numCellsLocal, keyMaxSlots);
+        SPH_COUNT(L);
+    }
+    k_slab_scan_bound<<<1, 32, 0, L.stream>>>(keyMaxSlots, guardCells, (uint32_t)numCellsLocal);
     SPH_COUNT(L);
 }
 
