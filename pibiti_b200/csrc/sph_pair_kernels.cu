@@ -188,12 +188,49 @@ __device__ __forceinline__ int row_cells(const uint32_t* __restrict__ cellStart,
     return ncell;
 }
 
+// the same table entries held in registers (no indexed array, which would live in local memory)
+struct RowCells { uint32_t b0, b1, b2, b3;  int ncell; };
+
+__device__ __forceinline__ RowCells load_row_cells(const uint32_t* __restrict__ cellStart, long long hb, long long C)
+{
+    RowCells rc;
+    long long c0 = hb - 1, c1 = hb + 1;
+    if (c0 < 0) c0 = 0;
+    if (c1 > C - 1) c1 = C - 1;
+    rc.ncell = c0 > c1 ? 0 : (int)(c1 - c0) + 1;
+    rc.b0 = rc.ncell > 0 ? __ldg(cellStart + c0) : 0u;
+    rc.b1 = rc.ncell > 0 ? __ldg(cellStart + c0 + 1) : 0u;
+    rc.b2 = rc.ncell > 1 ? __ldg(cellStart + c0 + 2) : 0u;
+    rc.b3 = rc.ncell > 2 ? __ldg(cellStart + c0 + 3) : 0u;
+    return rc;
+}
+
 // ---- density -------------------------------------------------------------------------------------
 
 // r2 exactly as the CPU evaluates "p.x*p.x + p.y*p.y + p.z*p.z" (no contraction)
 __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz)
 {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// The same value with the x and y lanes evaluated by the packed f32x2 pipe (FADD2 / FMUL2: per-lane IEEE
+// round-to-nearest, so bit-identical): 4 issue slots instead of 6 for the differences and squares.  pxy = {p.x, p.y}.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+
+__device__ __forceinline__ float dist2_exact_packed(unsigned long long pxy, float pz, const float4& q)
+{
+    unsigned long long d, m;
+    float xx, yy;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pxy), "l"(pack_f32x2(q.x, q.y)));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(m) : "l"(d));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(xx), "=f"(yy) : "l"(m));
+    const float dz = __fsub_rn(pz, q.z);
+    return __fadd_rn(__fadd_rn(xx, yy), __fmul_rn(dz, dz));
 }
 
 // Per-thread neighbour list under construction: column `tid` of a [kMax][T] uint16 array in shared
@@ -567,7 +604,11 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
 // segment).  Left to the compiler the store becomes a branch around five address instructions per candidate.
 // (Measured alternative, profiles/: lists built in shared memory and written with one TMA bulk store need fewer
 // instructions but 25 KB of shared memory per CTA; the lost occupancy costs more than the instructions save.)
-__global__ void __launch_bounds__(256)
+// 8 CTAs of 256 threads = every warp slot of an SM: the walk is latency-bound, so the register budget is 32
+#ifndef SPH_DENSITY_MIN_BLOCKS
+#define SPH_DENSITY_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, SPH_DENSITY_MIN_BLOCKS)
 k_density_l1(const __grid_constant__ SimParams par, int kMax,
              const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
              const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
@@ -578,7 +619,6 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const int i = first + blockIdx.x * T + threadIdx.x;
     if (i >= n) return;
     const float4 p4 = posS[i];
-    const float4 v4 = velS[i];
     const uint32_t key = keyS[i];
     const bool trunc = __ldg(maxCount) > par.maxParInCell;
     const float3 pi = make_float3(p4.x, p4.y, p4.z);
@@ -589,21 +629,21 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
     const uint32_t rowBytes = (uint32_t)T * 4u;
     const uint32_t endOff = (uint32_t)kMax * rowBytes;
     uint32_t off = threadIdx.x * 4u;
+    const unsigned long long pxy = pack_f32x2(pi.x, pi.y);
 
     float sum = 0.f;
     auto span = [&](uint32_t a, uint32_t e) {
         #pragma unroll 4
         for (uint32_t g = a; g < e; g++) {
             const float4 q = __ldg(posS + g);
-            const float r2 = dist2_exact(pi.x - q.x, pi.y - q.y, pi.z - q.z);
+            const float r2 = dist2_exact_packed(pxy, pi.z, q);
             const bool hit = r2 < h2;
             const float c = __fsub_rn(h2, r2);
             sum = hit ? fmaf(c * c, c, sum) : sum;              // one predicated FFMA
-            // the store is predicated, not branched around: the address is formed unconditionally
-            const uint32_t keep = hit && off < endOff;
-            asm volatile("{ .reg .pred p;  setp.ne.u32 p, %2, 0;  @p st.global.u32 [%0], %1; }"
-                         :: "l"(lb + off), "r"(g), "r"(keep));
-            off += hit ? rowBytes : 0u;
+            // store and advance are predicated, not branched around: the address is formed unconditionally
+            asm volatile("{ .reg .pred h, k;  setp.ne.u32 h, %3, 0;  setp.lt.and.u32 k, %0, %4, h;\n"
+                         "  @k st.global.u32 [%1], %2;  @h add.u32 %0, %0, %5; }"
+                         : "+r"(off) : "l"(lb + off), "r"(g), "r"((uint32_t)hit), "r"(endOff), "r"(rowBytes));
         }
     };
     auto run = [&](uint32_t a, uint32_t e) {
@@ -620,19 +660,30 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
             a = an;  e = en;  ok = okn;
         }
     } else {
+        // some cell holds more than maxParInCell particles: a row is still one run unless one of ITS cells overflows.
+        // The next row's four table entries are in flight while this row is walked.
+        const uint32_t mp = par.maxParInCell;
+        RowCells cur = load_row_cells(cellStart, row_hash(par, key, 0), C), nxt = cur;
         #pragma unroll 1
         for (int r = 0; r < kRows; r++) {
-            uint32_t b[4];  bool over;
-            const int ncell = row_cells(cellStart, row_hash(par, key, r), C, par.maxParInCell, b, over);
-            if (ncell == 0) continue;
-            if (!over) { run(b[0], b[ncell]);  continue; }
-            #pragma unroll
-            for (int k = 0; k < 3; k++)
-                if (k < ncell) run(b[k], min(b[k + 1], b[k] + par.maxParInCell));
+            if (r + 1 < kRows) nxt = load_row_cells(cellStart, row_hash(par, key, r + 1), C);
+            if (cur.ncell > 0) {
+                const bool over = cur.b1 - cur.b0 > mp || (cur.ncell > 1 && cur.b2 - cur.b1 > mp) || (cur.ncell > 2 && cur.b3 - cur.b2 > mp);
+                if (!over) {
+                    const uint32_t e = cur.ncell == 3 ? cur.b3 : cur.ncell == 2 ? cur.b2 : cur.b1;
+                    if (r == 4) run(cur.b0, e); else span(cur.b0, e);
+                } else {
+                    run(cur.b0, min(cur.b1, cur.b0 + mp));
+                    if (cur.ncell > 1) run(cur.b1, min(cur.b2, cur.b1 + mp));
+                    if (cur.ncell > 2) run(cur.b2, min(cur.b3, cur.b2 + mp));
+                }
+            }
+            cur = nxt;
         }
     }
     const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
     const float pres = (dens - par.restDensity) * par.stiffness;
+    const float4 v4 = velS[i];                  // not needed before: keeping it live across the walk costs registers
     posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
     velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
     const uint32_t cnt = (off - threadIdx.x * 4u) / rowBytes;
