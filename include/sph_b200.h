@@ -106,6 +106,17 @@ int sph_get_array_device(sph_t* s, int which, float* d_out, int start, int count
 int sph_device_buffers(sph_t* s, const float** d_pos, const float** d_vel, const uint32_t** d_index,
                        const uint32_t** d_cellStart /* numCells+1 entries */);
 
+/* ---- OpenGL interop ------------------------------------------------
+ * The reference keeps positions and colours in GL vertex buffers that its renderer draws (posVbo / colorVbo,
+ * SPH_Mem.cpp:20-37; ParticleRenderer::setVertexBuffer / setColorBuffer, render_particles.cpp:54-81).  Here the
+ * renderer keeps ownership of its buffers: register them once, then sph_gl_update after a step writes the arrays
+ * (original particle order, float4 per particle) into them on the device -- map, un-permute, unmap, no host copy.
+ * `which` is SPH_POS or SPH_COLOR (colour needs sph_set_visual(s, 1)); glBuffer = 0 unregisters.  The calling thread
+ * needs a current GL context on the handle's device; without one the call fails with SPH_ERR_CUDA.
+ * NOT exercised by the tests: the build and GPU boxes have no GL. */
+int sph_gl_register(sph_t* s, int which, unsigned int glBuffer);
+int sph_gl_update(sph_t* s);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 int sph_debug_dump(sph_t* s, int what, void* out, size_t outBytes);      /* blocking */
 int sph_get_timings(sph_t* s, float* msPerStage /*[SPH_STAGE_COUNT]*/, int enable);

@@ -53,6 +53,7 @@ struct sph_system {
         int workBound = 0;                  // launch bound for kernels over the work set
         SimParams parLocal;                 // par with numCells = numCellsLocal, for the neighbour walk
     } slab;
+    cudaGraphicsResource* glRes[2] = {nullptr, nullptr};    // registered GL buffers: positions, colours
     uint32_t* counters = nullptr;           // device: 4 append counters
     uint32_t* keyMax = nullptr;             // device: slab scan bound (sph_device.cuh kKeyMaxSlots)
     uint32_t* hostInts = nullptr;           // pinned: read-back of counters / cell-table entries
@@ -110,6 +111,7 @@ extern "C" int sph_destroy(sph_t* s)
                     s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->keyMax, s->clr, s->dye};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& r : s->glRes) if (r) cudaGraphicsUnregisterResource(r);
     if (s->hostInts) cudaFreeHost(s->hostInts);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->evForce) if (e) cudaEventDestroy(e);
@@ -354,6 +356,47 @@ extern "C" int sph_get_array_device(sph_t* s, int which, float* d_out, int start
     default: return fail(s, SPH_ERR_ARG, "sph_get_array: array %d not available", which);
     }
     CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+// cuda_gl_interop.h needs the GL headers, which this image does not have; the entry point lives in libcudart
+extern "C" cudaError_t CUDARTAPI cudaGraphicsGLRegisterBuffer(cudaGraphicsResource** resource, unsigned int buffer, unsigned int flags);
+
+extern "C" int sph_gl_register(sph_t* s, int which, unsigned int glBuffer)
+{
+    if (!s || (which != SPH_POS && which != SPH_COLOR)) return SPH_ERR_ARG;
+    CU_TRY(s, cudaSetDevice(s->device));
+    cudaGraphicsResource*& res = s->glRes[which == SPH_POS ? 0 : 1];
+    if (res) { CU_TRY(s, cudaStreamSynchronize(s->stream));  CU_TRY(s, cudaGraphicsUnregisterResource(res));  res = nullptr; }
+    if (glBuffer == 0) return SPH_OK;
+    cudaError_t e = cudaGraphicsGLRegisterBuffer(&res, glBuffer, cudaGraphicsRegisterFlagsWriteDiscard);
+    if (e != cudaSuccess) {
+        res = nullptr;
+        cudaGetLastError();
+        return fail(s, SPH_ERR_CUDA, "sph_gl_register: cudaGraphicsGLRegisterBuffer(%u) failed: %s (is a GL context current?)",
+                    glBuffer, cudaGetErrorString(e));
+    }
+    return SPH_OK;
+}
+
+extern "C" int sph_gl_update(sph_t* s)
+{
+    if (!s) return SPH_ERR_ARG;
+    CU_TRY(s, cudaSetDevice(s->device));
+    const int n = (int)s->par.numParticles;
+    for (int k = 0; k < 2; k++) {
+        if (!s->glRes[k]) continue;
+        if (k == 1 && !(s->visual && s->stepped)) continue;     // colours exist only after a visual step
+        void* p = nullptr;  size_t bytes = 0;
+        CU_TRY(s, cudaGraphicsMapResources(1, &s->glRes[k], s->stream));
+        cudaError_t e = cudaGraphicsResourceGetMappedPointer(&p, &bytes, s->glRes[k]);
+        int rc = SPH_OK;
+        if (e != cudaSuccess) rc = fail(s, SPH_ERR_CUDA, "sph_gl_update: %s", cudaGetErrorString(e));
+        else if (bytes < (size_t)n * sizeof(float4)) rc = fail(s, SPH_ERR_ARG, "sph_gl_update: GL buffer holds %zu bytes, %zu needed", bytes, (size_t)n * sizeof(float4));
+        else rc = sph_get_array_device(s, k == 0 ? SPH_POS : SPH_COLOR, (float*)p, 0, n);
+        CU_TRY(s, cudaGraphicsUnmapResources(1, &s->glRes[k], s->stream));
+        if (rc != SPH_OK) return rc;
+    }
     return SPH_OK;
 }
 

@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_set_visual", "sph_step", "sph_sync",
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
-    "sph_version",
+    "sph_version", "sph_gl_register", "sph_gl_update",
     "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack",
     "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
     "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_stats",
@@ -118,6 +118,8 @@ def load() -> C.CDLL:
     lib.sph_get_array_device.argtypes = [vp, ci, vp, ci, ci]
     lib.sph_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.sph_debug_dump.argtypes = [vp, ci, vp, C.c_size_t]
+    lib.sph_gl_register.argtypes = [vp, ci, C.c_uint]
+    lib.sph_gl_update.argtypes = [vp]
     lib.sph_get_timings.argtypes = [vp, vp, ci]
     lib.sph_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.sph_cuda_stream.argtypes = [vp]
