@@ -157,6 +157,9 @@ int sph_slab_pack_dp(sph_t* s, float* d_down, float* d_up, int capRows, int* cou
 int sph_slab_ghost_counts(sph_t* s, int* counts2 /* rows expected from below, from above */);
 int sph_slab_unpack_dp(sph_t* s, const float* d_below, int nBelow, const float* d_above, int nAbove);
 int sph_slab_force(sph_t* s);
+/* The same in two parts, so that the rho,p exchange can overlap the bulk of the force pass: part 1 = particles with no
+ * ghost neighbours (needs only sph_slab_density), part 2 = the rest (after sph_slab_unpack_dp); part 0 = both. */
+int sph_slab_force_part(sph_t* s, int part);
 /* diagnostics after a step: {largest real cell, work-set size, ghosts below, owned, ghosts above, retired slots} */
 int sph_slab_stats(sph_t* s, int* out6);
 

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -747,17 +748,44 @@ extern "C" int sph_slab_unpack_dp(sph_t* s, const float* d_below, int nBelow, co
     return SPH_OK;
 }
 
-extern "C" int sph_slab_force(sph_t* s)
+// part 0: all owned particles.  part 1: the CTAs whose particles all lie strictly between the first and the last owned
+// layer -- they have no ghost neighbours, so they do not need the rho,p rows of sph_slab_unpack_dp and can run while
+// that exchange is in flight.  part 2: the remaining CTAs.  (TMA variant: part 1 is empty, part 2 is everything.)
+extern "C" int sph_slab_force_part(sph_t* s, int part)
 {
     SLAB_CHECK(s);
     sph_system::Slab& b = s->slab;
     if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_force: call sph_slab_sort first");
-    if (s->timing) cudaEventRecord(s->evForce[0], s->stream);
-    sph_launch_force(launcher(s), s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
-                     s->nlist, s->ncount, s->ctaRows, s->vel, b.first, b.count);
-    if (sph_needs_obstacles(s->par)) sph_launch_obstacles(launcher(s), b.parLocal, s->posP, s->velD, s->vel, b.first, b.count);
-    if (s->timing) cudaEventRecord(s->evForce[1], s->stream);
-    s->stepped = true;
+    if (part < 0 || part > 2) return SPH_ERR_ARG;
+    SphLaunch L = launcher(s);
+    const int T = s->cfg.threads, blocks = (int)sph_pair_blocks(s->cfg, b.count);
+    int cLo = 0, cHi = blocks;                  // interior CTAs [cLo, cHi)
+    if (s->cfg.mode == SPH_PAIR_TMA) cHi = 0;
+    else {
+        if (b.hasLower) cLo = (b.bLoEnd - b.g0 + T - 1) / T;
+        if (b.hasUpper) cHi = (b.bHiStart - b.g0) / T;
+        if (cLo > blocks) cLo = blocks;
+        if (cHi < cLo) cHi = cLo;
+    }
+    auto run = [&](int c0, int c1) {            // force (+ obstacles) on CTAs [c0, c1)
+        if (c1 <= c0) return;
+        sph_launch_force(L, s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount,
+                         s->nlist, s->ncount, s->ctaRows, s->vel, b.first, b.count, c0, c1 - c0);
+        if (sph_needs_obstacles(s->par)) {
+            const int p0 = b.first + c0 * T, p1 = std::min(b.first + b.count, b.first + c1 * T);
+            sph_launch_obstacles(L, b.parLocal, s->posP, s->velD, s->vel, p0, p1 - p0);
+        }
+    };
+    if (s->timing && part != 2) cudaEventRecord(s->evForce[0], s->stream);
+    if (part == 0) run(0, blocks);
+    else if (part == 1) run(cLo, cHi);
+    else { run(0, cLo);  run(cHi, blocks); }
+    if (part != 1) {
+        if (s->timing) cudaEventRecord(s->evForce[1], s->stream);
+        s->stepped = true;
+    }
     CU_TRY(s, cudaGetLastError());
     return SPH_OK;
 }
+
+extern "C" int sph_slab_force(sph_t* s) { return sph_slab_force_part(s, 0); }

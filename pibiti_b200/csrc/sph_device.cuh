@@ -90,7 +90,8 @@ void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimP
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
-                      const uint32_t* ctaRows, float4* velOut, int first, int count);
+                      const uint32_t* ctaRows, float4* velOut, int first, int count,
+                      int ctaFirst = 0, int ctaCount = -1 /* L1 variant: only CTAs [ctaFirst, ctaFirst+ctaCount) of the range */);
 
 // ---- sph_extras_kernels.cu --------------------------------------------------------------------
 bool sph_needs_obstacles(const SimParams& par);        // height map or rotor configured

@@ -708,11 +708,12 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
            const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
            const uint32_t* __restrict__ nlist, const uint16_t* __restrict__ ncount,
-           float4* __restrict__ velOut, int first, int n)
+           float4* __restrict__ velOut, int first, int n, int ctaFirst)
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
-    const int i = first + blockIdx.x * T + threadIdx.x;
+    const int cta = blockIdx.x + ctaFirst;     // a launch may cover a sub-range of the CTAs the density launch used
+    const int i = first + cta * T + threadIdx.x;
     if (i >= n) return;
     const float4 pp = posP[i];
     const float4 vd = velD[i];
@@ -727,7 +728,7 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
     if (cnt != kListInvalid) {
         const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
         // list entries are consumed four at a time; the next four are in flight while these are evaluated
-        const uint32_t* lst = nlist + (size_t)blockIdx.x * kMax * T + threadIdx.x;
+        const uint32_t* lst = nlist + (size_t)cta * kMax * T + threadIdx.x;
         const uint32_t groups = (cnt + 3) >> 2;
         auto load4 = [&](uint32_t q) {
             const uint32_t t0 = 4 * q;
@@ -814,19 +815,24 @@ static bool force_list_streaming()
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
-                      const uint32_t* ctaRows, float4* velOut, int first, int count)
+                      const uint32_t* ctaRows, float4* velOut, int first, int count, int ctaFirst, int ctaCount)
 {
     if (count <= 0) return;
     const int n = first + count;
     int blocks = (int)sph_pair_blocks(cfg, count);
+    if (cfg.mode != SPH_PAIR_TMA && ctaCount >= 0) {            // sub-range of the CTAs (slab mode: interior / boundary)
+        if (ctaFirst < 0 || ctaFirst + ctaCount > blocks) ctaCount = blocks - ctaFirst;
+        if (ctaCount <= 0) return;
+        blocks = ctaCount;
+    } else ctaFirst = 0;
     if (cfg.mode == SPH_PAIR_TMA)
         k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
                                                                     (const uint16_t*)nlist, ncount, ctaRows, velOut, first, n);
     else if (force_list_streaming())
         k_force_l1<true><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                               (const uint32_t*)nlist, ncount, velOut, first, n);
+                                                               (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst);
     else
         k_force_l1<false><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                                (const uint32_t*)nlist, ncount, velOut, first, n);
+                                                                (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst);
     SPH_COUNT(L);
 }

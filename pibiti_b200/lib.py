@@ -84,7 +84,7 @@ ABI_SYMBOLS = (
     "sph_version", "sph_gl_register", "sph_gl_update",
     "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack",
     "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
-    "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_stats",
+    "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_force_part", "sph_slab_stats",
 )
 
 
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
     lib.sph_slab_ghost_counts.argtypes = [vp, ip]
     lib.sph_slab_unpack_dp.argtypes = [vp, vp, ci, vp, ci]
     lib.sph_slab_force.argtypes = [vp]
+    lib.sph_slab_force_part.argtypes = [vp, ci]
     lib.sph_slab_stats.argtypes = [vp, ip]
     _lib = lib
     return lib

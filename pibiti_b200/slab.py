@@ -198,6 +198,13 @@ class GpuSlabBackend:
     def force(self):
         self._check(self.L.sph_slab_force(self.h), "sph_slab_force")
 
+    def force_interior(self):
+        """Particles without ghost neighbours: needs density() only, so it can run while rho,p rows are exchanged."""
+        self._check(self.L.sph_slab_force_part(self.h, 1), "sph_slab_force_part(interior)")
+
+    def force_boundary(self):
+        self._check(self.L.sph_slab_force_part(self.h, 2), "sph_slab_force_part(boundary)")
+
     def sync(self):
         self.sys.sync()
 
@@ -228,6 +235,12 @@ class LocalComm:
             res.append((below, above))
         return res
 
+    def exchange_begin(self, backends, outs, empty, expected=None):
+        return self.exchange(backends, outs, empty, expected)
+
+    def exchange_end(self, pending):
+        return pending
+
 
 class DistComm:
     """One rank per process: nearest-neighbour send/recv over torch.distributed.
@@ -242,7 +255,32 @@ class DistComm:
         self.nccl = dist.get_backend() == "nccl"
         self.bytes_sent = 0
 
-    def exchange(self, backends, outs, empty, expected=None):
+    def exchange_begin(self, backends, outs, empty, expected=None):
+        """Start the exchange without making the solver's stream wait for it.  NCCL: the operations run on a second
+        stream that first waits for everything enqueued on the solver's stream so far (the packing kernels); whatever
+        the caller enqueues on the solver's stream before exchange_end overlaps the transfer.  gloo: synchronous."""
+        if not self.nccl:
+            return self.exchange(backends, outs, empty, expected)
+        t, be = self.torch, backends[0]
+        if getattr(be, "comm_stream", None) is None:
+            with t.cuda.device(be.device):
+                be.comm_stream = t.cuda.Stream(device=be.device)
+        ready = t.cuda.Event()
+        ready.record(be.stream)
+        be.comm_stream.wait_event(ready)
+        res = self.exchange(backends, outs, empty, expected, stream=be.comm_stream)
+        done = t.cuda.Event()
+        done.record(be.comm_stream)
+        return (res, done, be)
+
+    def exchange_end(self, pending):
+        if not self.nccl:
+            return pending
+        res, done, be = pending
+        be.stream.wait_event(done)
+        return res
+
+    def exchange(self, backends, outs, empty, expected=None, stream=None):
         """outs[0] = (to lower, to upper).  Fixed-size messages when `expected` is None (receive buffers have the
         senders' shape); otherwise expected[0] = (rows from below, rows from above)."""
         t, dist = self.torch, self.dist
@@ -255,7 +293,7 @@ class DistComm:
         width = down.shape[1]
         n_below, n_above = (down.shape[0], up.shape[0]) if expected is None else expected[0]
         if self.nccl:
-            ctx = t.cuda.stream(be.stream)
+            ctx = t.cuda.stream(stream if stream is not None else be.stream)
             dev = down.device
         else:
             ctx = _NullCtx()
@@ -330,13 +368,18 @@ def slab_step(backends, comm, prof: dict | None = None):
         b.density()
     outs = [b.pack_dp() for b in backends]
     lap("density+pack rho,p")
-    inc = comm.exchange(backends, outs, lambda b: b.empty_dp(), [b.expected_dp() for b in backends])
-    lap("exchange rho,p")
+    # the rho,p rows only matter to particles in the first / last owned layer: everything else is evaluated while
+    # the rows are in flight
+    pending = comm.exchange_begin(backends, outs, lambda b: b.empty_dp(), [b.expected_dp() for b in backends])
+    for b in backends:
+        b.force_interior()
+    inc = comm.exchange_end(pending)
+    lap("exchange rho,p + interior force")
     for b, (below, above) in zip(backends, inc):
         b.unpack_dp(below, above)
     for b in backends:
-        b.force()
-    lap("force")
+        b.force_boundary()
+    lap("boundary force")
 
 
 def split_initial_state(par, pos, vel, ranks, min_layers=2):
@@ -394,8 +437,7 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     stream = be.stream
 
     prof = {} if os.environ.get("SPH_SLAB_PROFILE") else None
-    if prof is not None:
-        be.sys.enable_timings(True)
+    be.sys.enable_timings(True)                  # event records around the pair kernels: no synchronisation
 
     def one_step():
         s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
@@ -405,6 +447,8 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     warm = max(args.warmup, 3)
     for _ in range(warm):
         one_step()
+    if prof is not None:
+        prof.clear()                             # NCCL connection set-up happened in the first exchange
     be.sync()
     dist.barrier()
     torch.cuda.synchronize()
@@ -425,6 +469,8 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     wall = time.perf_counter() - t0
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = be.sys.launch_count() - l0
+    kernel_ms = {k: v for k, v in be.sys.timings().items() if v >= 0}      # last timed step, this rank
+    owned_timed = be.n_owned
     clocks = sampler.stop() if rank == 0 else None
     owned = torch.tensor([be.n_owned], device="cuda", dtype=torch.int64)
     counts = [torch.zeros_like(owned) for _ in range(world)]
@@ -471,10 +517,18 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
                 "steps": e2e_steps, "api": "per rank: owned records pinned host -> device, slab step, device -> pinned host"},
         "gpu_launches": int(launches),
         "halo_bytes_per_step_rank0": comm.bytes_sent // max(args.steps + warm + e2e_steps, 1),
-        "phase_ms_by_rank": _gather_profile(dist, prof, args.steps + warm + e2e_steps, world,
+        "phase_ms_by_rank": _gather_profile(dist, prof, args.steps + e2e_steps, world,
                                              {"kernel_ms_last_step": {k: round(v, 3) for k, v in be.sys.timings().items() if v >= 0},
                                               "stats": be.stats()})
         if prof is not None else None,
         "roofline": None,
     }
+    dom = max((k for k in ("density", "force") if k in kernel_ms), key=lambda k: kernel_ms[k], default=None)
+    if dom is not None and kernel_ms[dom] > 0:
+        achieved = stage_bytes[dom] * owned_timed / (kernel_ms[dom] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": {"density": "k_density_l1", "force": "k_force_l1"}[dom],
+                           "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                           "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_particle": stage_bytes[dom],
+                           "note": "rank 0, last timed step, owned particles only; the single-GPU line carries the ncu traffic",
+                           "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()}}
     return out
