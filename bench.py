@@ -220,7 +220,7 @@ def run_ours_single(args) -> dict:
 # measured with `ncu --set full` on "tank 8M drop" (profiles/r01_*_l1.txt): dram__bytes_read.sum + dram__bytes_write.sum
 # per launch.  Both pair kernels move ~3x their algorithmic bytes because of the neighbour lists (8.4M x ~27 x 4 B =
 # 0.9 GB written by density, read by force) -- the price of a force kernel with a third of the instructions.
-TRAFFIC_BYTES: dict = {"force": 1_373_744_288, "density": 1_544_683_688}
+TRAFFIC_BYTES: dict = {"force": 1_363_952_864, "density": 1_573_461_464}
 
 
 def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> dict:

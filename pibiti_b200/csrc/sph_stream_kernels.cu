@@ -273,18 +273,21 @@ k_scan_reduce(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tileSums,
     if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the tile sums in place; tileSums[numTiles] = grand total
+// single block: exclusive scan of the tile sums in place, 16 per thread per round; tileSums[numTiles] = grand total
 __global__ void __launch_bounds__(256)
 k_scan_tiles(uint32_t* __restrict__ tileSums, int numTiles, uint32_t* __restrict__ maxCount)
 {
     __shared__ uint32_t total;
     uint32_t carry = 0;
     if (threadIdx.x == 0) *maxCount = 0;
-    for (int base = 0; base < numTiles; base += 256) {
-        int i = base + threadIdx.x;
-        uint32_t v = i < numTiles ? tileSums[i] : 0u;
-        uint32_t ex = block_excl_scan_256(v, &total);
-        if (i < numTiles) tileSums[i] = carry + ex;
+    for (int base = 0; base < numTiles; base += 4096) {
+        const int i0 = base + threadIdx.x * 16;
+        uint32_t v[16], s = 0;
+        #pragma unroll
+        for (int k = 0; k < 16; k++) { v[k] = i0 + k < numTiles ? tileSums[i0 + k] : 0u;  s += v[k]; }
+        uint32_t ex = carry + block_excl_scan_256(s, &total);
+        #pragma unroll
+        for (int k = 0; k < 16; k++) { if (i0 + k < numTiles) tileSums[i0 + k] = ex;  ex += v[k]; }
         carry += total;
         __syncthreads();
     }
@@ -336,7 +339,8 @@ k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const
     // largest cell population (decides whether the neighbour walk must truncate)
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxCount, mx);
+    // only when it would raise the value: same-address atomics serialise in L2
+    if ((threadIdx.x & 31) == 0 && mx > *reinterpret_cast<volatile uint32_t*>(maxCount)) atomicMax(maxCount, mx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -440,6 +444,20 @@ __device__ __forceinline__ int z_cell(const SimParams& par, float z)
     return (int)floorf((z - par.worldMin.z) / par.cellSize.z);
 }
 
+// Append to a message section: one atomic per warp instead of one per record (the boundary layers are contiguous
+// runs of the sorted state, so whole warps append together and same-address atomics serialise in L2).  Every lane
+// of the warp must call it.
+__device__ __forceinline__ uint32_t warp_append_slot(uint32_t* ctr, bool pred)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) return 0u;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
 // owned particles [first, n): those whose z-cell left [zLo, zHi) are copied out and retired
 __global__ void __launch_bounds__(256)
 k_slab_take_leavers(const __grid_constant__ SimParams par, const float4* __restrict__ pos, const float4* __restrict__ vel,
@@ -447,21 +465,21 @@ k_slab_take_leavers(const __grid_constant__ SimParams par, const float4* __restr
                     SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
                     uint32_t* __restrict__ ctrDown, uint32_t* __restrict__ ctrUp)
 {
-    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t id = idx[i];
-    if (id == kDeadIndex) return;
-    const float4 p = pos[i];
-    const int zc = z_cell(par, p.z);
-    SlabRecord* dst = nullptr;  int cap = 0;  uint32_t* ctr = nullptr;
-    if (zc < zLo && hasLower) { dst = down;  cap = capDown;  ctr = ctrDown; }
-    else if (zc >= zHi && hasUpper) { dst = up;  cap = capUp;  ctr = ctrUp; }
-    if (!dst) return;
-    const uint32_t slot = atomicAdd(ctr, 1u);
-    if (slot < (uint32_t)cap) {
-        SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(id, 0u, 0u, 0u);
-        dst[slot] = r;
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n && idx[i] != kDeadIndex;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool goDown = false, goUp = false;
+    if (live) {
+        p = pos[i];
+        const int zc = z_cell(par, p.z);
+        goDown = zc < zLo && hasLower;
+        goUp = zc >= zHi && hasUpper;
     }
+    const uint32_t slotDown = warp_append_slot(ctrDown, goDown), slotUp = warp_append_slot(ctrUp, goUp);
+    if (!(goDown || goUp)) return;
+    SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(idx[i], 0u, 0u, 0u);
+    if (goDown) { if (slotDown < (uint32_t)capDown) down[slotDown] = r; }
+    else if (slotUp < (uint32_t)capUp) up[slotUp] = r;
     idx[i] = kDeadIndex;
 }
 
@@ -472,22 +490,21 @@ k_slab_boundary(const __grid_constant__ SimParams par, const float4* __restrict_
                 SlabRecord* __restrict__ down, int capDown, SlabRecord* __restrict__ up, int capUp,
                 uint32_t* __restrict__ ctrDown, uint32_t* __restrict__ ctrUp)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t id = idx[i];
-    if (id == kDeadIndex) return;
-    const float4 p = pos[i];
-    const int zc = z_cell(par, p.z);
-    if (zc < zLo || zc >= zHi) return;              // a ghost left over in the work set: not ours to export
-    SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(id, 0u, 0u, 0u);
-    if (zc == zLo && hasLower) {
-        uint32_t slot = atomicAdd(ctrDown, 1u);
-        if (slot < (uint32_t)capDown) down[slot] = r;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n && idx[i] != kDeadIndex;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool toDown = false, toUp = false;
+    if (live) {
+        p = pos[i];
+        const int zc = z_cell(par, p.z);            // a ghost left over in the work set (outside [zLo,zHi)) is not ours to export
+        toDown = zc == zLo && hasLower;
+        toUp = zc == zHi - 1 && hasUpper && zc >= zLo;
     }
-    if (zc == zHi - 1 && hasUpper) {
-        uint32_t slot = atomicAdd(ctrUp, 1u);
-        if (slot < (uint32_t)capUp) up[slot] = r;
-    }
+    const uint32_t slotDown = warp_append_slot(ctrDown, toDown), slotUp = warp_append_slot(ctrUp, toUp);
+    if (!(toDown || toUp)) return;
+    SlabRecord r;  r.pos = p;  r.vel = vel[i];  r.meta = make_uint4(idx[i], 0u, 0u, 0u);
+    if (toDown && slotDown < (uint32_t)capDown) down[slotDown] = r;
+    if (toUp && slotUp < (uint32_t)capUp) up[slotUp] = r;
 }
 
 __global__ void __launch_bounds__(256)
