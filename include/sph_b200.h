@@ -149,6 +149,8 @@ int sph_slab_set_owned(sph_t* s, const float* d_records, int count);            
 int sph_slab_get_owned(sph_t* s, float* d_records, int capacity, int* count);    /* blocking */
 int sph_slab_integrate(sph_t* s);
 int sph_slab_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int capL, int capB);
+/* sph_slab_integrate + sph_slab_pack in one pass over the state (same results, one kernel instead of four) */
+int sph_slab_integrate_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int capL, int capB);
 int sph_slab_unpack(sph_t* s, const float* d_inBelow, const float* d_inAbove,
                     const float* d_ownDown, const float* d_ownUp, int capL, int capB);
 int sph_slab_sort(sph_t* s, int* counts3 /* ghosts below, owned, ghosts above */);    /* blocking */

@@ -611,6 +611,26 @@ extern "C" int sph_slab_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int cap
     return SPH_OK;
 }
 
+// sph_slab_integrate followed by sph_slab_pack, as one kernel: the state is read and written once
+extern "C" int sph_slab_integrate_pack(sph_t* s, float* d_msgDown, float* d_msgUp, int capL, int capB)
+{
+    SLAB_CHECK(s);
+    sph_system::Slab& b = s->slab;
+    if (!d_msgDown || !d_msgUp || capL < 1 || capB < 1) return SPH_ERR_ARG;
+    CU_TRY(s, cudaMemsetAsync(d_msgDown, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+    CU_TRY(s, cudaMemsetAsync(d_msgUp, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+    const int work = b.work;
+    b.work = b.first + b.count;                 // the slots behind the owned range are retired by the kernel
+    sph_launch_slab_integrate_pack(launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], b.first, b.count, work,
+                                   b.zLo, b.zHi, b.hasLower, b.hasUpper,
+                                   d_msgDown + SPH_SLAB_RECORD_FLOATS, d_msgUp + SPH_SLAB_RECORD_FLOATS, capL,
+                                   d_msgDown + (size_t)SPH_SLAB_RECORD_FLOATS * (1 + capL),
+                                   d_msgUp + (size_t)SPH_SLAB_RECORD_FLOATS * (1 + capL), capB,
+                                   reinterpret_cast<uint32_t*>(d_msgDown), reinterpret_cast<uint32_t*>(d_msgUp));
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
 extern "C" int sph_slab_unpack(sph_t* s, const float* d_inBelow, const float* d_inAbove,
                                const float* d_ownDown, const float* d_ownUp, int capL, int capB)
 {

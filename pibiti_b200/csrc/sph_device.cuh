@@ -65,6 +65,11 @@ void sph_launch_slab_boundary(const SphLaunch& L, const SimParams& par, const fl
 void sph_launch_slab_append(const SphLaunch& L, const void* recs, int count, float4* pos, float4* vel, uint32_t* idx, int at);
 void sph_launch_slab_export(const SphLaunch& L, const float4* pos, const float4* vel, const uint32_t* idx,
                             const float4* posP, const float4* velD, int first, int count, void* recs);
+// sph_slab_integrate + sph_slab_pack in one pass over the work set (headers zeroed by the caller)
+void sph_launch_slab_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                    int first, int count, int work, int zLo, int zHi, int hasLower, int hasUpper,
+                                    void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
+                                    uint32_t* headDown, uint32_t* headUp);
 void sph_launch_fill_u32(const SphLaunch& L, uint32_t* p, uint32_t v, int first, int count);
 void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const float4* pos, const uint32_t* idx,
                                uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int nMax, const uint32_t* nDev,

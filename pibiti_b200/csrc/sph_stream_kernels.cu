@@ -169,17 +169,9 @@ __device__ __forceinline__ uint32_t cell_hash(const SimParams& par, float3 p)
     return (uint32_t)(gz * (int)par.gridSize_yx + gy * (int)par.gridSize.x + gx);
 }
 
-__global__ void __launch_bounds__(256)
-k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
-                 float4* __restrict__ pos, float4* __restrict__ vel,
-                 uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU,
-                 uint32_t* __restrict__ cellCount, int first, int n)
+// boundary impulse -> gravity -> damping -> position -> hard clamp (step order Q6)
+__device__ __forceinline__ void integrate_particle(const SimParams& par, const BoundaryCtx& ctx, float3& p, float3& v)
 {
-    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p4 = pos[i], v4 = vel[i];
-    float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
-
     soft_boundary(par, ctx, p, v);
 
     const float dt = par.timeStep;                                  // System.cu:177-179
@@ -194,6 +186,21 @@ k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
     if (p.y < par.worldMin.y + hb) p.y = par.worldMin.y + hb;
     if (p.z > par.worldMax.z - hb) p.z = par.worldMax.z - hb;
     if (p.z < par.worldMin.z + hb) p.z = par.worldMin.z + hb;
+
+}
+
+__global__ void __launch_bounds__(256)
+k_integrate_hash(const __grid_constant__ SimParams par, const BoundaryCtx ctx,
+                 float4* __restrict__ pos, float4* __restrict__ vel,
+                 uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU,
+                 uint32_t* __restrict__ cellCount, int first, int n)
+{
+    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p4 = pos[i], v4 = vel[i];
+    float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
+
+    integrate_particle(par, ctx, p, v);
 
     pos[i] = make_float4(p.x, p.y, p.z, p4.w);
     vel[i] = make_float4(v.x, v.y, v.z, v4.w);
@@ -507,6 +514,52 @@ k_slab_boundary(const __grid_constant__ SimParams par, const float4* __restrict_
     if (toUp && slotUp < (uint32_t)capUp) up[slotUp] = r;
 }
 
+// sph_slab_integrate + sph_slab_pack in one pass over the work set [0, work): slots outside the owned range
+// [first, first+count) are retired (last step's ghosts); owned particles are integrated, and on the way out a particle
+// whose z cell left [zLo, zHi) moves into the neighbour's leaver section (and is retired here), while one in the first
+// or last owned layer leaves a copy in the neighbour's boundary section.
+__global__ void __launch_bounds__(256)
+k_slab_integrate_pack(const __grid_constant__ SimParams par, const BoundaryCtx ctx, float4* __restrict__ pos,
+                      float4* __restrict__ vel, uint32_t* __restrict__ idx, int first, int count, int work,
+                      int zLo, int zHi, int hasLower, int hasUpper,
+                      SlabRecord* __restrict__ leavDown, SlabRecord* __restrict__ leavUp, int capL,
+                      SlabRecord* __restrict__ bndDown, SlabRecord* __restrict__ bndUp, int capB,
+                      uint32_t* __restrict__ headDown, uint32_t* __restrict__ headUp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool owned = i >= first && i < first + count;
+    if (i < work && !owned) idx[i] = kDeadIndex;
+    uint32_t id = kDeadIndex;
+    float4 pOut = make_float4(0.f, 0.f, 0.f, 0.f), vOut = pOut;
+    bool goDown = false, goUp = false, copyDown = false, copyUp = false;
+    if (owned) {
+        id = idx[i];
+        const float4 p4 = pos[i], v4 = vel[i];
+        float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
+        integrate_particle(par, ctx, p, v);
+        pOut = make_float4(p.x, p.y, p.z, p4.w);
+        vOut = make_float4(v.x, v.y, v.z, v4.w);
+        pos[i] = pOut;
+        vel[i] = vOut;
+        if (id != kDeadIndex) {
+            const int zc = z_cell(par, p.z);
+            goDown = zc < zLo && hasLower;
+            goUp = zc >= zHi && hasUpper;
+            copyDown = zc == zLo && hasLower;
+            copyUp = zc == zHi - 1 && hasUpper && zc >= zLo;
+        }
+    }
+    const uint32_t sLeavDown = warp_append_slot(headDown + 0, goDown), sLeavUp = warp_append_slot(headUp + 0, goUp);
+    const uint32_t sBndDown = warp_append_slot(headDown + 1, copyDown), sBndUp = warp_append_slot(headUp + 1, copyUp);
+    if (!(goDown || goUp || copyDown || copyUp)) return;
+    SlabRecord r;  r.pos = pOut;  r.vel = vOut;  r.meta = make_uint4(id, 0u, 0u, 0u);
+    if (goDown) { if (sLeavDown < (uint32_t)capL) leavDown[sLeavDown] = r; }
+    else if (goUp) { if (sLeavUp < (uint32_t)capL) leavUp[sLeavUp] = r; }
+    if (goDown || goUp) idx[i] = kDeadIndex;
+    if (copyDown && sBndDown < (uint32_t)capB) bndDown[sBndDown] = r;
+    if (copyUp && sBndUp < (uint32_t)capB) bndUp[sBndUp] = r;
+}
+
 __global__ void __launch_bounds__(256)
 k_slab_append(const SlabRecord* __restrict__ recs, int count, float4* __restrict__ pos, float4* __restrict__ vel,
               uint32_t* __restrict__ idx, int at)
@@ -634,6 +687,20 @@ void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4*
     BoundaryCtx ctx;
     ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
     k_integrate_hash<<<blocks_for(count, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, keyU, rankU, cellCount, first, first + count);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                    int first, int count, int work, int zLo, int zHi, int hasLower, int hasUpper,
+                                    void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
+                                    uint32_t* headDown, uint32_t* headUp)
+{
+    if (work <= 0) return;
+    BoundaryCtx ctx;
+    ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
+    k_slab_integrate_pack<<<blocks_for(work, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, first, count, work, zLo, zHi,
+                                                                        hasLower, hasUpper, (SlabRecord*)leavDown, (SlabRecord*)leavUp, capL,
+                                                                        (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp);
     SPH_COUNT(L);
 }
 

@@ -82,7 +82,7 @@ ABI_SYMBOLS = (
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
     "sph_version", "sph_gl_register", "sph_gl_update",
-    "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack",
+    "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack", "sph_slab_integrate_pack",
     "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
     "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_force_part", "sph_slab_stats",
 )
@@ -141,6 +141,7 @@ def load() -> C.CDLL:
     lib.sph_slab_unpack_dp.argtypes = [vp, vp, ci, vp, ci]
     lib.sph_slab_force.argtypes = [vp]
     lib.sph_slab_force_part.argtypes = [vp, ci]
+    lib.sph_slab_integrate_pack.argtypes = [vp, vp, vp, ci, ci]
     lib.sph_slab_stats.argtypes = [vp, ip]
     _lib = lib
     return lib

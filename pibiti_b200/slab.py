@@ -166,6 +166,12 @@ class GpuSlabBackend:
                     "sph_slab_pack")
         return self.msg_down, self.msg_up
 
+    def integrate_pack(self):
+        """integrate() + pack() as one kernel."""
+        self._check(self.L.sph_slab_integrate_pack(self.h, self._p(self.msg_down), self._p(self.msg_up), self.caps.leavers,
+                                                   self.caps.boundary), "sph_slab_integrate_pack")
+        return self.msg_down, self.msg_up
+
     def unpack(self, below, above):
         b, a = self._dev(below), self._dev(above)
         self._keep = (b, a)             # the launch is asynchronous: keep the sources alive
@@ -354,9 +360,12 @@ def slab_step(backends, comm, prof: dict | None = None):
             prof[name] = prof.get(name, 0.0) + now - t[0]
             t[0] = now
 
-    for b in backends:
-        b.integrate()
-    outs = [b.pack() for b in backends]
+    if all(hasattr(b, "integrate_pack") for b in backends) and not os.environ.get("SPH_SLAB_SPLIT_PACK"):
+        outs = [b.integrate_pack() for b in backends]
+    else:
+        for b in backends:
+            b.integrate()
+        outs = [b.pack() for b in backends]
     lap("integrate+pack")
     inc = comm.exchange(backends, outs, lambda b: b.empty_message())
     lap("exchange particles")

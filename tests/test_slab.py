@@ -161,6 +161,13 @@ def test_gpu_slabs_equal_single_gpu(title, ranks, variant, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_gpu_slabs_split_integrate_and_pack_calls(monkeypatch):
+    """The separate sph_slab_integrate / sph_slab_pack entry points (slab_step uses the fused one by default)."""
+    monkeypatch.setenv("SPH_SLAB_SPLIT_PACK", "1")
+    test_gpu_slabs_equal_single_gpu("mini waves", 3, "l1,128,1344,48", monkeypatch)
+
+
+@pytest.mark.gpu
 def test_gpu_two_process_gloo_slabs_equal_single_gpu(tmp_path):
     steps = 6
     got = run_workers("gpu", "mini waves", steps, tmp_path)
