@@ -275,8 +275,9 @@ def run_reference(args) -> dict:
     o.step(args.steps)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = (f"{args.steps} steps of '{sample_title}' ({n} particles): the 1/8-scale member of the '{title}' scene family; "
-              "particle-updates/s is intensive in N")
+    sample = f"{args.steps} steps of '{sample_title}' ({n} particles)"
+    if sample_title != title:
+        sample += f": the 1/8-scale member of the '{title}' scene family; particle-updates/s is intensive in N"
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
