@@ -1,0 +1,87 @@
+"""Static checks of the built CUDA library (no GPU needed): the properties of the hot kernels that the parity and the
+performance arguments in DESIGN.md section 4 lean on, read from the SASS that actually ships."""
+from __future__ import annotations
+
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from pibiti_b200 import lib
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+pytestmark = pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not available")
+
+
+def _run(*args) -> str:
+    return subprocess.run([CUOBJDUMP, *args, str(lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+
+
+@pytest.fixture(scope="module")
+def sass() -> dict:
+    """function name (mangled) -> list of SASS instruction strings"""
+    out, cur = {}, None
+    for line in _run("-sass").splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = out.setdefault(m.group(1), [])
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+        if m and cur is not None:
+            cur.append(m.group(1).strip())
+    return out
+
+
+@pytest.fixture(scope="module")
+def resources() -> dict:
+    out, cur = {}, None
+    for line in _run("-res-usage").splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", line)
+        if m and cur:
+            out[cur] = dict(zip(("reg", "stack", "shared", "local"), map(int, m.groups())))
+    return out
+
+
+def _one(table: dict, needle: str):
+    hits = [k for k in table if needle in k]
+    assert hits, f"no kernel matching {needle}"
+    return [table[k] for k in hits]
+
+
+def test_library_is_sm_100a_only():
+    archs = set(re.findall(r"sm_\d+a?", _run("-lelf")))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_density_kernel_is_packed_predicated_and_register_lean(sass, resources):
+    (code,) = _one(sass, "12k_density_l1")
+    text = "\n".join(code)
+    assert "FADD2" in text and "FMUL2" in text          # x,y differences and squares on the packed f32x2 pipe
+    assert "FFMA2" not in text                          # ... and never contracted: r2 < h2 must stay bit-exact
+    assert re.search(r"@!?P\d STG\.E ", text)            # the list store is a predicated instruction
+    assert not any(i.startswith(("STL", "LDL")) for i in code)      # no local memory anywhere in the walk
+    (res,) = _one(resources, "12k_density_l1")
+    assert res["reg"] <= 32 and res["stack"] == 0 and res["local"] == 0
+
+
+def test_force_kernel_register_budget(resources):
+    for res in _one(resources, "10k_force_l1"):
+        assert res["reg"] <= 64 and res["stack"] == 0
+
+
+def test_staged_variant_uses_tma_bulk_copies(sass):
+    for name in ("9k_densityE", "7k_forceE"):
+        (code,) = _one(sass, name)
+        assert any(i.startswith("UBLKCP") or " UBLKCP" in i for i in code), name     # cp.async.bulk
+
+
+def test_streaming_kernels_have_no_local_memory(resources):
+    # (the integrate kernels index a float3 by axis in the cylinder / pump boundary branches: 32 bytes of stack there)
+    for needle in ("k_rank_gather", "k_bucket", "k_scan_apply", "k_scan_reduce", "k_slab_hash_hist"):
+        for res in _one(resources, needle):
+            assert res["stack"] == 0 and res["local"] == 0, needle
