@@ -1,0 +1,37 @@
+"""The reference arm of bench.py runs on the host alone, so its JSON line can be checked without a GPU."""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config"}
+
+
+def _run(env_extra=None, *args):
+    env = dict(os.environ, **(env_extra or {}))
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "mini box",
+                        "--steps", "2", "--warmup", "1", *args], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_prints_one_contract_line():
+    (line,) = _run()
+    d = json.loads(line)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "particle-updates/sec per SPH step" and d["unit"] == "particle-updates/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "mini box"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_under_torchrun_only_rank_zero_prints():
+    assert len(_run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")) == 1
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2") == []
