@@ -421,6 +421,9 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     import torch.distributed as dist
     from . import host
 
+    # `bench.py --slab` without torchrun: a one-rank job still needs the env:// rendezvous variables
+    for k, v in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0"), ("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29533")):
+        os.environ.setdefault(k, v)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
