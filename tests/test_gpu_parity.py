@@ -499,3 +499,31 @@ def test_gl_interop_fails_cleanly_without_a_gl_context():
         "s.Update(2); print('ok', rc)\n" % str(ROOT))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("variant", ["l1", "tma"])
+@pytest.mark.parametrize("n", [1, 37, 1000, 4097])
+def test_ragged_particle_counts(oracle_port, n, variant, monkeypatch):
+    """the reference's kernels do not bounds-check and need N to be a multiple of 512; these do, for any N
+    (the port oracle loops over particles, so it takes any N too)."""
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
+    h = host.CSph(device=-1)
+    par = h.scene_params(h.scene_index("mini dense cells")).copy()
+    ex = h.scene_extra(h.scene_index("mini dense cells"))
+    par["numParticles"] = n
+    pos, vel = _scene_fill(par, ex, n, 77 + n)
+    h.close()
+    g = lib.SphSystem(par, 0)
+    o = oracle_port.system(par)
+    for t in (g, o):
+        t.set_array(lib.SPH_POS, pos)
+        t.set_array(lib.SPH_VEL, vel)
+    for _ in range(3):
+        g.step(1)
+        o.step(1)
+        check_integers_exact(g, o)
+        check_floats(g, o, par)
+        g.set_array(lib.SPH_POS, o.get_array(0))          # resync: the next step starts from the oracle's floats
+        g.set_array(lib.SPH_VEL, o.get_array(1))
+    g.close()
+    o.close()
