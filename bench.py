@@ -212,6 +212,7 @@ def run_ours_single(args) -> dict:
                      "peak_source": hbm_src, "algorithmic_bytes_per_particle": STAGE_BYTES[dom],
                      "note": "density+force are FP32/shared-memory bound, not HBM bound (SURVEY.md D7); see fp32_frac",
                      "fp32_frac_density_force": round(PAIR_FLOP_PER_PARTICLE * n / pair_s / 1e12 / FP32_PEAK_TFLOPS, 4),
+                     "binding_unit_ncu": NCU_BINDING.get(dom),
                      "stages": stages},
     }
     return out, s
@@ -221,6 +222,13 @@ def run_ours_single(args) -> dict:
 # per launch.  Both pair kernels move ~3x their algorithmic bytes because of the neighbour lists (8.4M x ~27 x 4 B =
 # 0.9 GB written by density, read by force) -- the price of a force kernel with a third of the instructions.
 TRAFFIC_BYTES: dict = {"force": 1_363_952_864, "density": 1_573_461_464}
+# what actually bounds the two pair kernels (same captures): percentages of the sustained peak of the unit
+NCU_BINDING: dict = {
+    "density": {"l1tex_throughput_pct": 90.2, "issue_active_pct": 77.4, "dram_throughput_pct": 25.2, "warps_active_pct": 94.1,
+                "source": "profiles/r01_density_l1.txt"},
+    "force": {"l1tex_throughput_pct": 93.8, "issue_active_pct": 64.0, "dram_throughput_pct": 27.5, "warps_active_pct": 47.0,
+              "source": "profiles/r01_force_l1.txt"},
+}
 
 
 def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> dict:
