@@ -92,3 +92,44 @@ def test_product_never_touches_the_oracle():
                 assert pat not in text, f"{path} mentions {pat!r}"
     out = subprocess.run(["ldd", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sphport" not in out and "sphref" not in out
+
+
+APP_STYLE_CLIENT = r'''
+// Written the way the reference's App layer uses `App::psys` (grep 'psys->' source/App): direct access to scn.params,
+// scenes, curScene, hPos/hVel, and the cSPH methods -- compiled against include/sph_host.h only.
+#include <cstdio>
+#include <cmath>
+#include "sph_host.h"
+int main(int argc, char** argv)
+{
+    SphOptions opt = cSPH::LoadOptions(argv[1]);
+    cSPH* psys = new cSPH(argv[1], -1);                       // scene layer only: no GPU in this test
+    SimParams* p = &psys->scn.params;                         // Sliders.cpp binds slider pointers like this
+    printf("scenes %d cur %d n %u title %s windowed %d\n", (int)psys->scenes.size(), psys->curScene, p->numParticles,
+           psys->scn.title, (int)opt.bWindowed);
+    psys->NextScene(false);
+    psys->PrevScene(false);
+    psys->Reset(0);
+    psys->Drop(false);
+    psys->UpdateEmitter();
+    p->viscosity *= 2.f;  psys->app.bChangedAny = true;       // ParamBase::Changed()
+    float sum = 0.f;
+    for (unsigned i = 0; i < p->numParticles; i++) sum += psys->hPos[i].w;
+    printf("w-sum %.1f emitId %d\n", sum, psys->app.emitId);
+    int rc = psys->Update();                                  // must fail loudly: there is no CPU path
+    printf("update rc %d: %s\n", rc, psys->lastError());
+    delete psys;
+    return rc != 0 && std::isfinite(sum) ? 0 : 1;
+}
+'''
+
+
+def test_app_style_cpp_client_compiles_and_links_against_the_host_header(tmp_path):
+    src, exe = tmp_path / "client.cpp", tmp_path / "client"
+    src.write_text(APP_STYLE_CLIENT)
+    libdir = lib.LIB_PATH.parent
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", str(src),
+                    "-o", str(exe), f"-L{libdir}", "-lsph_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe), str(host.DEFAULT_SCENES_XML)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "scenes" in r.stdout and "update rc" in r.stdout and "update rc 0" not in r.stdout
