@@ -322,10 +322,6 @@ def main():
         out = slab.bench_multi(args, METRIC, UNIT, STAGE_BYTES, measured_peaks(), ClockSampler)
         if rank == 0:
             print(json.dumps(out), flush=True)
-        import torch.distributed as dist
-        if dist.is_initialized():
-            dist.barrier()
-            dist.destroy_process_group()
         return
 
     out, s = run_ours_single(args)
