@@ -80,10 +80,16 @@ int sph_destroy(sph_t* s);                                   /* cSPH::_FreeMem, 
  * numCells and gridSize must not exceed what sph_create allocated. */
 int sph_set_params(sph_t* s, const struct SimParams* params);
 int sph_get_params(sph_t* s, struct SimParams* out);
+/* Returns the handle to the state sph_create left it in (all particles at zero, slot order == original order)
+ * while keeping every allocation: cSPH::InitScene calls it when the next scene fits the buffers, where the
+ * reference frees and reallocates everything (SPH_Scenes.cpp:9-13, SPH_Mem.cpp:11-82). */
+int sph_reset_state(sph_t* s);
 
 /* Colour (System.cu:406-515) and dye (:519-545) are visual-only outputs of the reference's force kernel.  They
  * are off by default (no cost in the step); when enabled every step also fills SPH_COLOR / SPH_DYE. */
 int sph_set_visual(sph_t* s, int enable);
+/* dye concentrations (dDyeColor, System.cu:519-545), original particle order, from host memory (checkpoint restore) */
+int sph_set_dye(sph_t* s, const float* dye, int start, int count);
 
 /* ---- stepping ------------------------------------------------------------------------------ */
 /* nsteps x { integrate -> hash -> sort -> reorder -> density -> force }, the stage order of

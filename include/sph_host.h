@@ -8,8 +8,10 @@
 // Same member names and meaning, so code written against `psys->scn.params.*`, `psys->Update()`,
 // `psys->setArray(...)`, `psys->NextScene()` compiles against this header.  What differs, because
 // this layer is headless (no GL, no GLUT):
-//   * positions live in solver-owned device memory, not GL VBOs: getPosBuffer() returns a device
-//     pointer instead of a GL buffer id (posVbo/colorVbo do not exist);
+//   * positions live in solver-owned device memory.  The renderer keeps ownership of its GL buffers:
+//     registerGLBuffers(posVbo, colorVbo) hands their ids over once, Update() then refreshes them on the
+//     device after every step, and getPosBuffer() returns the position buffer's GL id exactly as the
+//     reference does (SPH.h:29).  Headless callers read getPosDevice() / getArray() instead;
 //   * the App:: statics the reference's SPH layer reaches into (App::emitId, App::dyePos,
 //     App::colliderPos, camera lag, ParamBase::bChangedAny) are members of cSPH::app;
 //   * errors are reported through lastError()/return codes instead of exit(1).
@@ -70,6 +72,17 @@ public:
     void _UpdateGrid();
 };
 
+// pch/timer.h:23-36: wall-clock timer the App layer reads through psys->tim (tim.FR, tim.dt;
+// App/RenderText.cpp:19,69,81).  The reference's body is QueryPerformanceCounter inside #if _WIN32 and
+// therefore dead on Linux; this one runs on std::chrono with the same fields.
+class Timer {
+    double st, st1;  int iFR;
+public:
+    double t, dt, FR, iv, iv1;      // time, delta time, frame rate, interval, frame-rate interval
+    Timer();
+    bool update(bool updFR = false);
+};
+
 // program options of the <Options> element (the reference stores them in App:: statics,
 // SPH_Scenes.cpp:99-109)
 struct SphOptions {
@@ -118,7 +131,12 @@ public:
 
     float4* getArray(bool pos);                 // NB inverted flag as in the reference: false = positions, true = velocities
     void setArray(bool pos, const float4* data, int start, int count);
-    const float4* getPosBuffer() const;         // device pointer (sorted order); reference returns a GL VBO id
+    uint getPosBuffer() const { return posVbo[curPosRead]; }    // GL id of the position buffer (SPH.h:29); 0 when headless
+    const float4* getPosDevice() const;         // device pointer of the live positions (sorted order), for headless callers
+    // Hands the renderer's GL buffers to the solver (the reference creates them itself in _InitMem,
+    // SPH_Mem.cpp:26-29).  Update() refreshes them after every step.  0 on success; without a current GL context
+    // the registration fails and the ids stay 0.
+    int registerGLBuffers(uint positionsVbo, uint colorsVbo);
 
     // Checkpoint / resume (the reference has none): parameters, positions and velocities in
     // original particle order, and the ring / rain / time counters.  0 on success.
@@ -129,6 +147,10 @@ public:
     const char* lastError() const { return err.c_str(); }
 
     float4 *hPos, *hVel;                        // host mirrors, original particle order
+    int* hCounters;                             // debug counters (SPH.h:43; always zero here, as in the reference's build)
+    uint posVbo[2], colorVbo;                   // GL ids handed over by registerGLBuffers (both posVbo entries are the same buffer)
+    uint curPosRead, curPosWrite;               // kept for source compatibility: positions do not ping-pong between VBOs here
+    Timer tim;                                  // updated once per Update(), SPH_Update.cpp:16
     SphAppState app;
 
 private:
@@ -136,6 +158,7 @@ private:
     int device;
     sph_t* sys;
     std::string err;
+    size_t memParticles, memCells;              // what the device buffers of `sys` were allocated for
 };
 
 #endif  // SPH_HOST_H

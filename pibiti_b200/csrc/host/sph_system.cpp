@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 
 namespace {
 
@@ -29,15 +30,48 @@ inline float len3(float x, float y, float z) { return sqrtf(x * x + y * y + z * 
 
 }  // namespace
 
-cSPH::cSPH(const char* scenesXmlPath, int dev)
-    : bInitialized(false), curScene(0), hPos(nullptr), hVel(nullptr),
-      xmlPath(scenesXmlPath ? scenesXmlPath : "Scenes.xml"), device(dev), sys(nullptr)
+// ---- timer (pch/timer.cpp:6-65, on a portable clock) ------------------------------------------------
+
+static double now_seconds()
 {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+Timer::Timer() : iFR(0), dt(0.), FR(0.), iv(0.), iv1(0.4)
+{
+    t = now_seconds();
+    st = t;  st1 = t;
+}
+
+bool Timer::update(bool updFR)
+{
+    t = now_seconds();
+    dt = t - st;
+    if (dt < iv) return false;          // not yet one interval
+    st = t;
+    if (!updFR) return true;
+    iFR++;
+    const double dt1 = t - st1;
+    if (dt1 >= iv1) { FR = iFR / dt1;  iFR = 0;  st1 = t; }
+    return true;
+}
+
+cSPH::cSPH(const char* scenesXmlPath, int dev)
+    : bInitialized(false), curScene(0), hPos(nullptr), hVel(nullptr), hCounters(nullptr), colorVbo(0),
+      curPosRead(0), curPosWrite(1), xmlPath(scenesXmlPath ? scenesXmlPath : "Scenes.xml"), device(dev), sys(nullptr),
+      memParticles(0), memCells(0)
+{
+    posVbo[0] = posVbo[1] = 0;
     DropPos = f3(0, 0, 0);
     LoadScenes();
 }
 
-cSPH::~cSPH() { _FreeMem(); }
+cSPH::~cSPH()
+{
+    _FreeMem();
+    if (sys) { sph_destroy(sys);  sys = nullptr; }
+}
 
 // ---- memory ------------------------------------------------------------------------------------
 
@@ -48,19 +82,28 @@ void cSPH::_InitMem()
     const size_t npar = scn.params.numParticles;
     hPos = new float4[npar];  memset(hPos, 0, npar * sizeof(float4));
     hVel = new float4[npar];  memset(hVel, 0, npar * sizeof(float4));
-    if (device >= 0) {
-        int rc = sph_create(&scn.params, device, &sys);
-        if (rc != SPH_OK) { err = sph_last_error(nullptr);  sys = nullptr;  fprintf(stderr, "cSPH: %s\n", err.c_str()); }
+    hCounters = new int[10];  memset(hCounters, 0, 10 * sizeof(int));     // SPH_Mem.cpp:24
+    if (device < 0) return;
+    // A scene that fits the device buffers of the previous one keeps them (the reference frees and reallocates
+    // everything on every scene switch, SPH_Scenes.cpp:9-13 -> SPH_Mem.cpp:11-82): only the parameters change.
+    if (sys && npar <= memParticles && scn.params.numCells <= memCells) {
+        if (sph_set_params(sys, &scn.params) == SPH_OK && sph_reset_state(sys) == SPH_OK) return;
+        err = sph_last_error(sys);
     }
+    if (sys) { sph_destroy(sys);  sys = nullptr;  posVbo[0] = posVbo[1] = colorVbo = 0; }
+    int rc = sph_create(&scn.params, device, &sys);
+    if (rc != SPH_OK) { err = sph_last_error(nullptr);  sys = nullptr;  memParticles = memCells = 0;  fprintf(stderr, "cSPH: %s\n", err.c_str()); }
+    else { memParticles = npar;  memCells = scn.params.numCells; }
 }
 
+// Host mirrors go; the device buffers stay with the handle until the object dies or a larger scene needs new ones.
 void cSPH::_FreeMem()
 {
     if (!bInitialized) return;
     bInitialized = false;
     delete[] hPos;  hPos = nullptr;
     delete[] hVel;  hVel = nullptr;
-    if (sys) { sph_destroy(sys);  sys = nullptr; }
+    delete[] hCounters;  hCounters = nullptr;
 }
 
 // ---- particle initialisers ---------------------------------------------------------------------
@@ -199,12 +242,28 @@ int cSPH::Update(int nsteps)
 {
     if (!bInitialized) return SPH_ERR_STATE;
     if (!sys) { if (err.empty()) err = "cSPH::Update: no solver (constructed without a device)";  return SPH_ERR_STATE; }
+    tim.update(true);                                       // SPH_Update.cpp:16
     if (app.bChangedAny) {                                  // SPH_Update.cpp:19-27
         app.bChangedAny = false;
         int rc = sph_set_params(sys, &scn.params);
         if (rc != SPH_OK) { err = sph_last_error(sys);  return rc; }
     }
     int rc = sph_step(sys, nsteps);
+    if (rc == SPH_OK && (posVbo[0] || colorVbo)) rc = sph_gl_update(sys);      // the renderer's buffers follow the step
+    if (rc != SPH_OK) err = sph_last_error(sys);
+    return rc;
+}
+
+int cSPH::registerGLBuffers(uint positionsVbo, uint colorsVbo)
+{
+    if (!sys) { err = "registerGLBuffers: no solver";  return SPH_ERR_STATE; }
+    int rc = sph_gl_register(sys, SPH_POS, positionsVbo);
+    if (rc == SPH_OK) { posVbo[0] = posVbo[1] = positionsVbo; }
+    if (rc == SPH_OK && colorsVbo) {
+        rc = sph_set_visual(sys, 1);
+        if (rc == SPH_OK) rc = sph_gl_register(sys, SPH_COLOR, colorsVbo);
+        if (rc == SPH_OK) colorVbo = colorsVbo;
+    }
     if (rc != SPH_OK) err = sph_last_error(sys);
     return rc;
 }
@@ -336,7 +395,7 @@ void cSPH::setArray(bool pos, const float4* data, int start, int count)
     if (data != mirror + start) memcpy(mirror + start, data, (size_t)count * sizeof(float4));
 }
 
-const float4* cSPH::getPosBuffer() const
+const float4* cSPH::getPosDevice() const
 {
     const float* d = nullptr;
     if (sys) sph_device_buffers(sys, &d, nullptr, nullptr, nullptr);
@@ -349,10 +408,15 @@ namespace {
 struct CheckpointHeader {
     char magic[8];              // "SPHB200\0"
     unsigned version, numParticles;
+    unsigned sizeofScene, sizeofParams;     // layout guard: a file written by another build is rejected
     int emitId, cntRain;
     float fSimTime;
     int curScene;
+    float4 colliderPos;         // App::colliderPos / App::dyePos: the targets the per-step prologue drags
+    float3 dyePos;              //   scn.params.collPos / dyePos towards (App/Update.cpp:28-61)
+    float3 camPosLag, camRotLag;
 };
+const unsigned kCheckpointVersion = 2;
 }
 
 int cSPH::SaveState(const char* path)
@@ -365,11 +429,21 @@ int cSPH::SaveState(const char* path)
     CheckpointHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, "SPHB200", 8);
-    h.version = 1;  h.numParticles = scn.params.numParticles;
+    h.version = kCheckpointVersion;  h.numParticles = scn.params.numParticles;
+    h.sizeofScene = (unsigned)sizeof(Scene);  h.sizeofParams = (unsigned)sizeof(SimParams);
     h.emitId = app.emitId;  h.cntRain = app.cntRain;  h.fSimTime = app.fSimTime;  h.curScene = curScene;
+    h.colliderPos = app.colliderPos;  h.dyePos = app.dyePos;  h.camPosLag = app.camPosLag;  h.camRotLag = app.camRotLag;
     const size_t n = scn.params.numParticles;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&scn, sizeof(Scene), 1, f) == 1 &&
               fwrite(pos, sizeof(float4), n, f) == n && fwrite(vel, sizeof(float4), n, f) == n;
+    if (ok && sys) {            // dye concentrations, when the visual outputs are on
+        std::vector<float> dye(n);
+        unsigned hasDye = sph_get_array(sys, SPH_DYE, dye.data(), 0, (int)n) == SPH_OK ? 1u : 0u;
+        ok = fwrite(&hasDye, sizeof hasDye, 1, f) == 1 && (!hasDye || fwrite(dye.data(), sizeof(float), n, f) == n);
+    } else if (ok) {
+        unsigned hasDye = 0;
+        ok = fwrite(&hasDye, sizeof hasDye, 1, f) == 1;
+    }
     fclose(f);
     if (!ok) { err = std::string("short write to ") + path;  return SPH_ERR_ARG; }
     return SPH_OK;
@@ -381,19 +455,38 @@ int cSPH::LoadState(const char* path)
     if (!f) { err = std::string("cannot read ") + path;  return SPH_ERR_ARG; }
     CheckpointHeader h;
     Scene saved;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SPHB200", 8) != 0 || h.version != 1 ||
-        fread(&saved, sizeof(Scene), 1, f) != 1 || saved.params.numParticles != h.numParticles) {
-        fclose(f);  err = std::string("not a checkpoint: ") + path;  return SPH_ERR_ARG;
-    }
+    auto reject = [&](const char* why) { fclose(f);  err = std::string(why) + ": " + path;  return SPH_ERR_ARG; };
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SPHB200", 8) != 0) return reject("not a checkpoint");
+    if (h.version != kCheckpointVersion || h.sizeofScene != sizeof(Scene) || h.sizeofParams != sizeof(SimParams))
+        return reject("checkpoint written by an incompatible build");
+    if (fread(&saved, sizeof(Scene), 1, f) != 1 || saved.params.numParticles != h.numParticles) return reject("not a checkpoint");
+    // the raw Scene block is only trusted after its indices and sizes have been checked
+    if (saved.ca < 0 || saved.ca >= SPH_NUM_ACC || saved.ce < 0 || saved.ce >= NumEmit || saved.params.numParticles == 0 ||
+        (unsigned long long)saved.params.gridSize.x * saved.params.gridSize.y * saved.params.gridSize.z != saved.params.numCells)
+        return reject("corrupt checkpoint (scene block)");
+    for (int e = 0; e < NumEmit; e++)
+        if (saved.emit[e].size < 0 || saved.emit[e].size > 10 || saved.emit[e].size2 < 0 || saved.emit[e].size2 > 10)
+            return reject("corrupt checkpoint (emitter sizes)");
+    saved.title[sizeof saved.title - 1] = 0;
     scn = saved;
     _FreeMem();  _InitMem();                                // buffers for the saved particle / cell counts
     const size_t n = h.numParticles;
     bool ok = fread(hPos, sizeof(float4), n, f) == n && fread(hVel, sizeof(float4), n, f) == n;
+    unsigned hasDye = 0;
+    std::vector<float> dye;
+    if (ok && fread(&hasDye, sizeof hasDye, 1, f) == 1 && hasDye) {
+        dye.resize(n);
+        ok = fread(dye.data(), sizeof(float), n, f) == n;
+    }
     fclose(f);
     if (!ok) { err = std::string("truncated checkpoint: ") + path;  return SPH_ERR_ARG; }
     setArray(0, hPos, 0, (int)n);
     setArray(1, hVel, 0, (int)n);
+    if (sys && hasDye) {
+        if (sph_set_visual(sys, 1) != SPH_OK || sph_set_dye(sys, dye.data(), 0, (int)n) != SPH_OK) { err = sph_last_error(sys);  return SPH_ERR_CUDA; }
+    }
     app.emitId = h.emitId;  app.cntRain = h.cntRain;  app.fSimTime = h.fSimTime;
+    app.colliderPos = h.colliderPos;  app.dyePos = h.dyePos;  app.camPosLag = h.camPosLag;  app.camRotLag = h.camRotLag;
     if (h.curScene >= 0 && h.curScene < (int)scenes.size()) curScene = h.curScene;
     app.bChangedAny = false;                                // _InitMem uploaded scn.params
     return sys || device < 0 ? SPH_OK : SPH_ERR_CUDA;

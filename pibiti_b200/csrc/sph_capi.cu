@@ -95,6 +95,7 @@ static const char* check_params(const SimParams* p)
     return nullptr;
 }
 
+static int check_range(sph_system* s, int start, int count);
 static SphLaunch launcher(sph_system* s) { SphLaunch L;  L.stream = s->stream;  L.launches = &s->launches;  return L; }
 
 template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
@@ -162,8 +163,13 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1,threads,cap,kMax" -- tuning / test aid
         char mode[8] = {0};  int t = 0, c = 0, k = 0;
         if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024 && k % 4 == 0) {
-            s->cfg.mode = strcmp(mode, "tma") == 0 ? SPH_PAIR_TMA : SPH_PAIR_L1;
-            s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
+            const bool tma = strcmp(mode, "tma") == 0;
+            // the staged variant keeps cap candidates (32 B each in the force kernel) and the list block in shared memory
+            const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : 0;
+            if (smemNeed <= prop.sharedMemPerBlockOptin) {
+                s->cfg.mode = tma ? SPH_PAIR_TMA : SPH_PAIR_L1;
+                s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
+            }
         }
     }
     ALLOC(s->pos[0], n);  ALLOC(s->pos[1], n);  ALLOC(s->vel, n);  ALLOC(s->velS, n);
@@ -176,23 +182,48 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
 #undef ALLOC
 
-    CU_TRY(nullptr, cudaMallocHost((void**)&s->hostInts, 64));
-    CU_TRY(nullptr, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto& ev : s->ev) CU_TRY(nullptr, cudaEventCreate(&ev));
-    for (auto& ev : s->evForce) CU_TRY(nullptr, cudaEventCreate(&ev));
+    // failures past this point release what was allocated (the handle, its buffers, stream and events)
+#define CREATE_TRY(call)                                                                               \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            int rc = fail(nullptr, SPH_ERR_CUDA, "sph_create: %s failed: %s", #call, cudaGetErrorString(_e)); \
+            cudaGetLastError();                                                                        \
+            sph_destroy(s);                                                                            \
+            return rc;                                                                                 \
+        }                                                                                              \
+    } while (0)
+    CREATE_TRY(cudaMallocHost((void**)&s->hostInts, 64));
+    CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& ev : s->ev) CREATE_TRY(cudaEventCreate(&ev));
+    for (auto& ev : s->evForce) CREATE_TRY(cudaEventCreate(&ev));
 
-    CU_TRY(nullptr, sph_pair_prepare(s->cfg));
+    CREATE_TRY(sph_pair_prepare(s->cfg));
     if (const char* env = getenv("SPH_B200_GRAPHS")) s->useGraphs = atoi(env) != 0;
 
-    CU_TRY(nullptr, cudaMemsetAsync(s->pos[0], 0, n * sizeof(float4), s->stream));
-    CU_TRY(nullptr, cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
-    CU_TRY(nullptr, cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
-    CU_TRY(nullptr, cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
-    CU_TRY(nullptr, cudaMemsetAsync(s->keyMax, 0, (kKeyMaxSlots + 8) * sizeof(uint32_t), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->pos[0], 0, n * sizeof(float4), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
+    // posP / velD rows of ghost slots are read by the filtering walk before the first rho,p exchange fills them
+    CREATE_TRY(cudaMemsetAsync(s->posP, 0, n * sizeof(float4), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->velD, 0, n * sizeof(float4), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->keyMax, 0, (kKeyMaxSlots + 8) * sizeof(uint32_t), s->stream));
     sph_launch_iota(launcher(s), s->idx[0], (int)n);
-    CU_TRY(nullptr, cudaStreamSynchronize(s->stream));
+    CREATE_TRY(cudaStreamSynchronize(s->stream));
+#undef CREATE_TRY
     *out = s;
     return SPH_OK;
+}
+
+// boundary effects a z-slab decomposition cannot honour: they move a particle further than one cell layer in a step
+static const char* slab_unsupported(const SimParams* p)
+{
+    if (p->bndEffZ == BND_EFF_WRAP || p->bndEffZ == BND_EFF_CYCLE)
+        return "slab mode does not support the Z wrap/cycle teleport (bndEffZ=1,2): it would make the first and last slab neighbours";
+    if (p->bndType == BND_PUMP_Y)
+        return "slab mode does not support the pump boundary (bndType=5): its exit->inlet teleport moves particles across slabs";
+    return nullptr;
 }
 
 extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
@@ -201,6 +232,25 @@ extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
     if (const char* why = check_params(p)) return fail(s, SPH_ERR_PARAMS, "sph_set_params: %s", why);
     if ((int)p->numParticles > s->nAlloc || (int)p->numCells > s->cellsAlloc)
         return fail(s, SPH_ERR_PARAMS, "sph_set_params: numParticles/numCells exceed the allocation of sph_create");
+    if (s->slab.on) {
+        if (p->numParticles != s->par.numParticles)
+            return fail(s, SPH_ERR_PARAMS, "sph_set_params: numParticles is the slab capacity and cannot change in slab mode");
+        if (const char* why = slab_unsupported(p)) return fail(s, SPH_ERR_PARAMS, "sph_set_params: %s", why);
+    }
+    if (p->numParticles != s->par.numParticles && s->stepped) {
+        // Slots are in sorted order after a step and idx[] is a permutation of the OLD particle range: bring the state
+        // back to original order first, so that the new range [0, numParticles) keeps exactly the particles the
+        // reference would keep (it simply runs its kernels over the first numParticles entries).
+        CU_TRY(s, cudaSetDevice(s->device));
+        const int nOld = (int)s->par.numParticles, cur = s->cur;
+        SphLaunch L = launcher(s);
+        sph_launch_unpermute4(L, s->pos[cur], s->idx[cur], s->pos[cur ^ 1], 0, nOld, nOld);
+        sph_launch_unpermute4(L, s->vel, s->idx[cur], s->velS, 0, nOld, nOld);
+        CU_TRY(s, cudaMemcpyAsync(s->vel, s->velS, (size_t)nOld * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        s->cur = cur ^ 1;
+        sph_launch_iota(L, s->idx[s->cur], s->nAlloc);
+        CU_TRY(s, cudaGetLastError());
+    }
     if (p->numCells != s->par.numCells || p->numParticles != s->par.numParticles) s->stepped = false;
     if (memcmp(&s->par, p, sizeof(SimParams)) != 0) { s->stateVersion++;  s->stepsSinceChange = 0; }
     s->par = *p;
@@ -208,6 +258,36 @@ extern "C" int sph_set_params(sph_t* s, const struct SimParams* p)
         s->slab.parLocal = *p;
         s->slab.parLocal.numCells = (uint)s->slab.numCellsLocal;
     }
+    return SPH_OK;
+}
+
+// Back to the state sph_create leaves behind (slot order == original order, nothing stepped), without touching
+// the allocation: what a scene switch needs when the new scene fits the buffers (cSPH::InitScene).
+extern "C" int sph_reset_state(sph_t* s)
+{
+    if (!s) return SPH_ERR_ARG;
+    if (s->slab.on) return fail(s, SPH_ERR_STATE, "sph_reset_state: handle is in slab mode");
+    CU_TRY(s, cudaSetDevice(s->device));
+    const size_t n = (size_t)s->nAlloc;
+    s->cur = 0;  s->stepped = false;  s->stateVersion++;  s->stepsSinceChange = 0;
+    CU_TRY(s, cudaMemsetAsync(s->pos[0], 0, n * sizeof(float4), s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->vel, 0, n * sizeof(float4), s->stream));
+    if (s->clr) CU_TRY(s, cudaMemsetAsync(s->clr, 0, n * sizeof(float4), s->stream));
+    if (s->dye) CU_TRY(s, cudaMemsetAsync(s->dye, 0, n * sizeof(float), s->stream));
+    sph_launch_iota(launcher(s), s->idx[0], (int)n);
+    CU_TRY(s, cudaGetLastError());
+    return SPH_OK;
+}
+
+// dye concentrations (dDyeColor, original particle order) from host memory: checkpoint restore
+extern "C" int sph_set_dye(sph_t* s, const float* dye, int start, int count)
+{
+    if (!s || !dye) return SPH_ERR_ARG;
+    if (int rc = check_range(s, start, count)) return rc;
+    if (!s->dye) return fail(s, SPH_ERR_STATE, "sph_set_dye: enable the visual outputs first (sph_set_visual)");
+    CU_TRY(s, cudaSetDevice(s->device));
+    CU_TRY(s, cudaMemcpyAsync(s->dye + start, dye, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
     return SPH_OK;
 }
 
@@ -533,8 +613,7 @@ extern "C" int sph_slab_configure(sph_t* s, int zLo, int zHi, int hasLower, int 
     const int gz = (int)s->par.gridSize.z;
     if (zLo < 0 || zHi > gz || zHi - zLo < 1) return fail(s, SPH_ERR_ARG, "sph_slab_configure: bad layer range [%d,%d) of %d", zLo, zHi, gz);
     if ((hasLower && zLo == 0) || (hasUpper && zHi == gz)) return fail(s, SPH_ERR_ARG, "sph_slab_configure: neighbour beyond the grid");
-    if (s->par.bndEffZ == BND_EFF_WRAP || s->par.bndEffZ == BND_EFF_CYCLE)
-        return fail(s, SPH_ERR_PARAMS, "slab mode does not support the Z wrap/cycle teleport (bndEffZ=1,2): it would make the first and last slab neighbours");
+    if (const char* why = slab_unsupported(&s->par)) return fail(s, SPH_ERR_PARAMS, "sph_slab_configure: %s", why);
     sph_system::Slab& b = s->slab;
     b.on = true;  b.zLo = zLo;  b.zHi = zHi;  b.hasLower = hasLower ? 1 : 0;  b.hasUpper = hasUpper ? 1 : 0;
     b.lowLayers = b.hasLower;  b.highLayers = b.hasUpper;

@@ -78,7 +78,7 @@ STAGE_NAMES = ("integrate_hash", "sort", "reorder", "density", "force")
 
 # every symbol include/sph_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
-    "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_set_visual", "sph_step", "sph_sync",
+    "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_reset_state", "sph_set_visual", "sph_set_dye", "sph_step", "sph_sync",
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
     "sph_version", "sph_gl_register", "sph_gl_update",
@@ -110,6 +110,8 @@ def load() -> C.CDLL:
     lib.sph_set_params.argtypes = [vp, vp]
     lib.sph_get_params.argtypes = [vp, vp]
     lib.sph_set_visual.argtypes = [vp, ci]
+    lib.sph_reset_state.argtypes = [vp]
+    lib.sph_set_dye.argtypes = [vp, vp, ci, ci]
     lib.sph_step.argtypes = [vp, ci]
     lib.sph_sync.argtypes = [vp]
     lib.sph_set_array.argtypes = [vp, ci, vp, ci, ci]
