@@ -37,6 +37,42 @@ METRIC = "particle-updates/sec per SPH step"
 UNIT = "particle-updates/s"
 # algorithmic bytes per particle per stage (SURVEY.md section 8d / BASELINE.md section 3)
 STAGE_BYTES = {"integrate_hash": 72, "sort": 24, "reorder": 72, "density": 24, "force": 56}
+CELL_TABLE_BYTES = 16                                        # per cell, sort stage: histogram R+zero, scan W, bucket R
+
+
+def stage_bytes(stage: str, n: int, cells: int) -> int:
+    """Algorithmic bytes one launch of the stage moves."""
+    return STAGE_BYTES[stage] * n + (CELL_TABLE_BYTES * cells if stage == "sort" else 0)
+
+
+def kernel_source_hash() -> str:
+    """Identifies the kernel sources an ncu capture belongs to (profiles/ncu_pair_kernels.json carries the same hash)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("sph_pair_kernels.cu", "sph_stream_kernels.cu", "sph_device.cuh"):
+        h.update((ROOT / "pibiti_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_evidence(stage: str, workload: str) -> dict:
+    """dram bytes per launch and the busiest unit of the stage's kernel, from the committed ncu summary of the SAME
+    kernel sources and workload (profiles/summarize.py writes it).  A capture of other sources is reported as stale
+    and contributes no number."""
+    p = ROOT / "profiles" / "ncu_pair_kernels.json"
+    if not p.exists():
+        return {"traffic": None, "stale": True, "why": "no profiles/ncu_pair_kernels.json"}
+    try:
+        d = json.loads(p.read_text())
+    except Exception as e:                                   # noqa: BLE001
+        return {"traffic": None, "stale": True, "why": f"unreadable: {e}"}
+    if d.get("source_hash") != kernel_source_hash():
+        return {"traffic": None, "stale": True, "why": "kernel sources changed since the capture", "capture_hash": d.get("source_hash")}
+    k = d.get("kernels", {}).get(stage)
+    if not k or d.get("workload") != workload:
+        return {"traffic": None, "stale": True, "why": f"no capture of {stage} on '{workload}' (have '{d.get('workload')}')"}
+    return {"traffic": k.get("dram_bytes"), "stale": False, "kernel": k.get("kernel"), "bound_unit": k.get("bound_unit"),
+            "units_pct": k.get("units_pct"), "l2_hit_pct": k.get("l2_hit_pct"), "l1_hit_pct": k.get("l1_hit_pct"),
+            "source": d.get("source")}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12            # non-tensor FP32, for context
 PAIR_FLOP_PER_PARTICLE = 2700                                # SURVEY.md 8d estimate for density+force
 
@@ -186,61 +222,58 @@ def run_ours_single(args) -> dict:
     assert np.isfinite(hvel.numpy()).all(), "non-finite velocities after the benchmark"
 
     hbm, hbm_src = measured_peaks()
-    # the dominant kernel is whichever pair kernel took longer in this run (density since the force kernel
-    # consumes neighbour lists)
+    cells = int(par["numCells"][0])
+    # the dominant kernel is whichever pair kernel took longer in this run
     dom = "density" if stage_ms["density"] >= stage_ms["force"] else "force"
-    dom_kernel = {"density": "k_density_l1 (density/pressure + neighbour-list build)",
-                  "force": "k_force_l1 (pair force over neighbour lists)"}[dom]
-    achieved = STAGE_BYTES[dom] * n / (stage_ms[dom] * 1e-3) / 1e9
-    stages = {k: {"ms": round(stage_ms[k], 4), "algorithmic_GBps": round(STAGE_BYTES[k] * n / (stage_ms[k] * 1e-3) / 1e9, 1),
-                  "hbm_frac": round(STAGE_BYTES[k] * n / (stage_ms[k] * 1e-3) / 1e9 / hbm, 4),
-                  "dram_traffic_bytes_ncu": TRAFFIC_BYTES.get(k)} for k in stage_ms}
+    ev = {k: ncu_evidence(k, title) for k in stage_ms}
+    gbps = {k: stage_bytes(k, n, cells) / (stage_ms[k] * 1e-3) / 1e9 for k in stage_ms}
+    stages = {k: {"ms": round(stage_ms[k], 4), "algorithmic_bytes": stage_bytes(k, n, cells), "algorithmic_GBps": round(gbps[k], 1),
+                  "hbm_frac": round(gbps[k] / hbm, 4), "dram_traffic_bytes_ncu": ev[k]["traffic"]} for k in stage_ms}
     pair_s = (stage_ms["density"] + stage_ms["force"]) * 1e-3
+    dom_ev = ev[dom]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": title, "particles": n, "grid": [int(x) for x in par["gridSize"][0]],
                    "scene_file": "scenes/Scenes.xml", "l2": "state (140 B/particle) is far larger than L2; no flush needed",
-                   "timing": "CUDA events on the solver stream"},
+                   "timing": "CUDA events on the solver stream", "pair_kernels": g.pair_variant()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
                 "steps": e2e_steps, "api": "cSPH setArray(pos,vel) -> Update -> getArray(pos,vel), pinned host buffers"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 1), "peak": hbm,
-                     "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": TRAFFIC_BYTES.get(dom),
+        # achieved / peak / frac are ALGORITHMIC HBM bytes over the measured copy bandwidth, as the contract asks;
+        # `bound` names the unit ncu shows busiest for this kernel (the pair kernels are not HBM-bound)
+        "roofline": {"bound": dom_ev.get("bound_unit") or "unknown (no current ncu capture)", "roofline_against": "hbm",
+                     "kernel": dom_ev.get("kernel") or dom, "achieved": round(gbps[dom], 1), "peak": hbm,
+                     "unit": "GB/s", "frac": round(gbps[dom] / hbm, 4), "traffic": dom_ev["traffic"],
+                     "traffic_stale": dom_ev["stale"], "traffic_note": dom_ev.get("why") or dom_ev.get("source"),
                      "peak_source": hbm_src, "algorithmic_bytes_per_particle": STAGE_BYTES[dom],
-                     "note": "density+force are FP32/shared-memory bound, not HBM bound (SURVEY.md D7); see fp32_frac",
                      "fp32_frac_density_force": round(PAIR_FLOP_PER_PARTICLE * n / pair_s / 1e12 / FP32_PEAK_TFLOPS, 4),
-                     "binding_unit_ncu": NCU_BINDING.get(dom),
+                     "units_pct_ncu": dom_ev.get("units_pct"), "l2_hit_pct_ncu": dom_ev.get("l2_hit_pct"),
                      "stages": stages},
     }
     return out, s
 
 
-# measured with `ncu --set full` on "tank 8M drop" (profiles/r01_*_l1.txt): dram__bytes_read.sum + dram__bytes_write.sum
-# per launch.  Both pair kernels move ~3x their algorithmic bytes because of the neighbour lists (8.4M x ~27 x 4 B =
-# 0.9 GB written by density, read by force) -- the price of a force kernel with a third of the instructions.
-TRAFFIC_BYTES: dict = {"force": 1_363_952_864, "density": 1_573_461_464}
-# what actually bounds the two pair kernels (same captures): percentages of the sustained peak of the unit
-NCU_BINDING: dict = {
-    "density": {"l1tex_throughput_pct": 90.2, "issue_active_pct": 77.4, "dram_throughput_pct": 25.2, "warps_active_pct": 94.1,
-                "source": "profiles/r01_density_l1.txt"},
-    "force": {"l1tex_throughput_pct": 93.8, "issue_active_pct": 64.0, "dram_throughput_pct": 27.5, "warps_active_pct": 47.0,
-              "source": "profiles/r01_force_l1.txt"},
-}
+def _host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> dict:
-    """The CPU oracle on this box's host cores, on a bounded sample of the workload."""
-    from oracle import oracle as orc                  # the one place bench.py executes oracle/
-    from pibiti_b200 import host
+def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) -> tuple[dict, dict]:
+    """The CPU oracle on this box's host cores, on a bounded sample of the workload -- and, because the oracle's
+    step is already paid for, the one-step parity bar of the workload the numbers are quoted on: oracle and GPU start
+    from the same state, both step once, integers must agree bit for bit and rho / v within 1e-5."""
+    from oracle import oracle as orc                  # the one place bench.py executes oracle/ (as the checker)
+    from pibiti_b200 import host, lib
     O = orc.load(None)
-    O.set_threads(threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
-    s = host.CSph(device=-1)
+    O.set_threads(threads or _host_threads())
+    s = host.CSph(device=0)
     s.select_scene(title)
     if "drop" in title:
         s.Drop(False)
+    if "wave" in title:
+        s.UpdateEmitter()
     par = s.params
     pos, vel = s.host_arrays()
     n = s.n
@@ -250,49 +283,118 @@ def cpu_baseline(title: str, threads: int | None = None, full_steps: int = 1) ->
     t0 = time.perf_counter()
     o.step(full_steps)
     dt = time.perf_counter() - t0
-    o.close()
-    s.close()
-    return {"value": n * full_steps / dt, "unit": UNIT, "cores": O.threads(), "kind": O.kind,
+    base = {"value": n * full_steps / dt, "unit": UNIT, "cores": O.threads(), "kind": O.kind,
             "sample": f"{full_steps} step(s) of '{title}' ({n} particles), OpenMP over emulated thread blocks",
             "seconds": round(dt, 2)}
 
+    check = {"config": title, "particles": n, "steps": full_steps, "oracle": O.kind, "ok": False}
+    try:
+        g = s.solver()
+        s.Update(full_steps)
+        REL = 1e-5
+        res = {
+            "sorted_pairs_bit_exact": bool(np.array_equal(g.dump(lib.DUMP_SORTED_PAIRS), o.dump(0))),
+            "cell_start_bit_exact": bool(np.array_equal(g.dump(lib.DUMP_CELL_START), o.dump(1))),
+            "neighbour_counts_bit_exact": bool(np.array_equal(g.dump(lib.DUMP_NEIGHBOR_COUNTS), o.dump(6))),
+            "positions_bit_exact": bool(np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0))),
+        }
+        dg, do = g.dump(lib.DUMP_DENSITY), o.dump(5)
+        res["density_max_rel_err"] = float(np.max(np.abs(dg - do) / np.maximum(np.abs(do), 1e-30)))
+        vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+        vmax = max(float(np.abs(vo[:, :3]).max()), 1e-3)
+        res["velocity_max_err_over_vmax"] = float(np.abs(vg - vo).max() / vmax)
+        res["tolerance"] = REL
+        check.update(res)
+        check["ok"] = bool(res["sorted_pairs_bit_exact"] and res["cell_start_bit_exact"] and res["neighbour_counts_bit_exact"]
+                           and res["positions_bit_exact"] and res["density_max_rel_err"] <= REL
+                           and res["velocity_max_err_over_vmax"] <= REL)
+    except Exception as e:                                   # noqa: BLE001
+        check["error"] = f"{type(e).__name__}: {e}"
+    o.close()
+    s.close()
+    return base, check
+
 
 def run_reference(args) -> dict:
-    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (its kernel text host-compiled,
+    oracle/_ref/libsphref.so), all host threads, on the SAME workload the GPU arm runs at this N, from the initial state
+    the reference's own scene code builds.  Nothing of pibiti_b200/ is loaded into this process."""
     n_gpus = args.gpus
     title = workload_for(n_gpus, args.workload)
-    # bounded sample: the 1M-particle member of the same scene family, so K+W steps end within minutes
-    sample_title = "Extreme box 1 M" if "tank 8M" in title else "wave tank 256k" if "wave" in title else title
     from oracle import oracle as orc
-    from pibiti_b200 import host
     O = orc.load(None)
-    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would serialise the baseline)
-    O.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    s = host.CSph(device=-1)
-    s.select_scene(sample_title)
-    if "drop" in title:
-        s.Drop(False)
-    par = s.params
-    pos, vel = s.host_arrays()
-    n = s.n
+    O.set_threads(_host_threads())
+    wave = "wave" in title
+    if O.kind == "reference":
+        from oracle.ref_scene import RefScene
+        sc = RefScene(ROOT / "scenes", title)
+        if "drop" in title:
+            sc.drop(False)
+        par = sc.params()
+        pos, vel = sc.arrays()
+        n = sc.n
+        prologue = sc.update_emitter if wave else None
+    else:                                               # no reference build on this box: the port, scene from the host layer
+        from pibiti_b200 import host
+        hs = host.CSph(device=-1)
+        hs.select_scene(title)
+        if "drop" in title:
+            hs.Drop(False)
+        par = hs.params
+        pos, vel = hs.host_arrays()
+        n = hs.n
+
+        def prologue():
+            hs.UpdateEmitter()
+            return hs.params
+        if not wave:
+            prologue = None
     o = O.system(par)
     o.set_array(0, pos)
     o.set_array(1, vel)
-    o.step(max(args.warmup, 1))
+    del pos, vel
+
+    def run(k):
+        for _ in range(k):
+            if prologue is not None:
+                o.set_params(prologue())
+            o.step(1)
+
+    # bounded in TIME, never in space: the workload is always the GPU arm's; when K+W steps of it would run for much longer
+    # than REF_BUDGET_S on these host cores (16M particles and up), fewer steps are timed and the line says how many
+    budget = float(os.environ.get("SPH_REF_BUDGET_S", "150"))
     t0 = time.perf_counter()
-    o.step(args.steps)
+    run(1)
+    first = time.perf_counter() - t0
+    warm = max(1, min(max(args.warmup, 1), int(0.2 * budget / first)))
+    run(warm - 1)
+    timed = max(1, min(args.steps, int(0.8 * budget / first)))
+    t0 = time.perf_counter()
+    run(timed)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = f"{args.steps} steps of '{sample_title}' ({n} particles)"
-    if sample_title != title:
-        sample += f": the 1/8-scale member of the '{title}' scene family; particle-updates/s is intensive in N"
+    value = n * timed / dt
+    sample = f"{timed} of {args.steps} steps of '{title}' ({n} particles): the full workload of the GPU arm, {warm} warm-up step(s)"
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps_timed": timed, "warmup": warm, "ms_per_step": dt / timed * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": title, "sample_scene": sample_title, "particles": n},
+            "config": {"workload": title, "particles": n, "scene_file": "scenes/Scenes.xml",
+                       "initial_state": "reference scene code (oracle/_ref)" if O.kind == "reference" else "host layer (port)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.threads(), "kind": O.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "native_so_loaded": repo_libraries_mapped()}
+
+
+def repo_libraries_mapped() -> list[str]:
+    """Shared libraries of this repository mapped into this process (the reference arm must show oracle/ only)."""
+    libs = set()
+    try:
+        for ln in open("/proc/self/maps"):
+            path = ln.split(None, 5)[-1].strip() if ln.count(" ") >= 5 else ""
+            if path.startswith(str(ROOT)) and ".so" in path:
+                libs.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(libs)
 
 
 def main():
@@ -327,7 +429,7 @@ def main():
     out, s = run_ours_single(args)
     if not args.no_cpu_baseline:
         s.close()
-        out["cpu_baseline"] = cpu_baseline(out["config"]["workload"])
+        out["cpu_baseline"], out["parity_check"] = cpu_baseline(out["config"]["workload"])
     print(json.dumps(out), flush=True)
 
 

@@ -131,6 +131,7 @@ int sph_kernel_launch_count(sph_t* s, long long* launches);             /* kerne
 void* sph_cuda_stream(sph_t* s);                                         /* cudaStream_t of the handle */
 const char* sph_last_error(sph_t* s);                                    /* s may be NULL: last create error */
 const char* sph_version(void);
+const char* sph_pair_variant(sph_t* s);                                   /* density/force kernel variant in use */
 
 /* ---- slab decomposition: one handle per GPU owns the z-cell layers [zLo, zHi) ------------------------
  * New in this library (the reference is single-GPU, source/App/App.cpp:142).  The grid is cut into

@@ -57,6 +57,17 @@ int  sphh_save_state(sphh_t* h, const char* path);                  /* checkpoin
 int  sphh_load_state(sphh_t* h, const char* path);
 void sphh_load_options(const char* scenesXmlPath, int* out7);
 
+/* state the reference keeps in App:: statics and the UI writes (App/Input.cpp): drag targets of the per-step
+ * prologue, emitter lag state, rain counter, ParamBase::bChangedAny */
+void sphh_set_targets(sphh_t* h, const float* collider4, const float* dye3, const float* acc3);
+void sphh_set_emitter(sphh_t* h, int e, const float* posLag3, const float* rotLag2, float vel, int size, int size2);
+int  sphh_cnt_rain(sphh_t* h);
+int  sphh_changed_flag(sphh_t* h, int clear);
+/* renderer hand-over: psys->colorVbo / getPosBuffer() (App/App.cpp:70, App/Render.cpp:12); psys->tim.FR */
+int  sphh_register_gl(sphh_t* h, unsigned posVbo, unsigned colorVbo);
+unsigned sphh_pos_buffer(sphh_t* h);
+double sphh_timer_fps(sphh_t* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ for f in Scene.cpp Scene_Load.cpp SPH_Init.cpp SPH_Scenes.cpp; do
 done
 # per-step host prologue (App::UpdateEmitter), for the "next" row N1
 grep -v '^[[:space:]]*#include' "$REF/source/App/Update.cpp" > "$GEN/App_Update.inc"
+sed -n '588,593p' "$REF/source/App/Input.cpp" > "$GEN/App_mulTr.inc"
 
 CXXFLAGS="-O2 -fopenmp -fPIC -std=c++14 -ffp-contract=off -w"
 INC="-I$HERE -I$GEN -I$CUDA_INC -I$REF/source/CUDA -I$REF/source/external -I$REF/source/external/cutil"

@@ -98,8 +98,12 @@ class OracleSystem:
     def __init__(self, orc: Oracle, par: np.ndarray):
         self.o = orc
         self.par = np.ascontiguousarray(par).copy()
-        self.n = int(self.par["numParticles"][0])
-        self.num_cells = int(self.par["numCells"][0])
+        if self.par.dtype == np.uint8:          # raw 560-byte SimParams block (include/sph_params.h offsets 4 and 56)
+            self.n = int(self.par[4:8].view(np.uint32)[0])
+            self.num_cells = int(self.par[56:60].view(np.uint32)[0])
+        else:
+            self.n = int(self.par["numParticles"][0])
+            self.num_cells = int(self.par["numCells"][0])
         self.h = C.c_void_p(orc.L.orc_create(_p(self.par)))
 
     def close(self):

@@ -104,6 +104,29 @@ sph_t* sphh_solver(sphh_t* h) { return S(h)->solver(); }
 int sphh_save_state(sphh_t* h, const char* path) { return S(h)->SaveState(path); }
 int sphh_load_state(sphh_t* h, const char* path) { return S(h)->LoadState(path); }
 
+// the targets the per-step prologue drags collPos / dyePos / acc[ca].pos towards (the reference's mouse handlers
+// write them, App/Input.cpp); null pointers leave a target alone
+void sphh_set_targets(sphh_t* h, const float* collider4, const float* dye3, const float* acc3)
+{
+    cSPH* s = S(h);
+    if (collider4) { s->app.colliderPos.x = collider4[0]; s->app.colliderPos.y = collider4[1]; s->app.colliderPos.z = collider4[2]; s->app.colliderPos.w = collider4[3]; }
+    if (dye3) { s->app.dyePos.x = dye3[0]; s->app.dyePos.y = dye3[1]; s->app.dyePos.z = dye3[2]; }
+    if (acc3) { float3& a = s->scn.accPos[s->scn.ca];  a.x = acc3[0]; a.y = acc3[1]; a.z = acc3[2]; }
+}
+void sphh_set_emitter(sphh_t* h, int e, const float* posLag3, const float* rotLag2, float vel, int size, int size2)
+{
+    if (e < 0 || e >= NumEmit) return;
+    Emitter& em = S(h)->scn.emit[e];
+    em.posLag.x = posLag3[0]; em.posLag.y = posLag3[1]; em.posLag.z = posLag3[2];
+    em.rotLag.x = rotLag2[0]; em.rotLag.y = rotLag2[1]; em.rotLag.z = 0.f;
+    em.vel = vel;  em.size = size;  em.size2 = size2;
+}
+int sphh_cnt_rain(sphh_t* h) { return S(h)->app.cntRain; }
+int sphh_changed_flag(sphh_t* h, int clear) { int v = S(h)->app.bChangedAny ? 1 : 0;  if (clear) S(h)->app.bChangedAny = false;  return v; }
+int sphh_register_gl(sphh_t* h, unsigned posVbo, unsigned colorVbo) { return S(h)->registerGLBuffers(posVbo, colorVbo); }
+unsigned sphh_pos_buffer(sphh_t* h) { return S(h)->getPosBuffer(); }
+double sphh_timer_fps(sphh_t* h) { return S(h)->tim.FR; }
+
 void sphh_load_options(const char* scenesXmlPath, int* out7)
 {
     SphOptions o = cSPH::LoadOptions(scenesXmlPath);

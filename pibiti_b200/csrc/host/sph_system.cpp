@@ -331,8 +331,10 @@ void cSPH::UpdateEmitter()
         const float spc = sc.spacing;
         float4 pos[100], vel[100];
 
-        const float ax = em.rotLag.x * (PI / 180.f), ay = -em.rotLag.y * (PI / 180.f);
-        const float ca = cosf(ax), sa = sinf(ax), cb = cosf(ay), sb = sinf(ay);
+        // glRotatef evaluates sine and cosine of angle*pi/180 in double and rounds to float (OpenGL's fixed-function
+        // matrix code, e.g. Mesa's _math_matrix_rotate); the same here so that the emitted particles are bit-identical
+        const double ax = (double)em.rotLag.x * (M_PI / 180.0), ay = (double)(-em.rotLag.y) * (M_PI / 180.0);
+        const float ca = (float)cos(ax), sa = (float)sin(ax), cb = (float)cos(ay), sb = (float)sin(ay);
         // columns of M = Rx(ax) * Ry(ay); the reference multiplies a vector by the columns
         const float c0[3] = {cb, sa * sb, -ca * sb}, c1[3] = {0.f, ca, sa}, c2[3] = {sb, -sa * cb, ca * cb};
         auto mulTr = [&](const float* v, float* rr) {

@@ -102,6 +102,15 @@ template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaM
 
 extern "C" const char* sph_version(void) { return "pibiti_b200 0.1 (sm_100a)"; }
 
+// which density/force kernel pair this handle launches, e.g. "l1,threads=128,kMax=48"
+extern "C" const char* sph_pair_variant(sph_t* s)
+{
+    if (!s) return "";
+    static thread_local char buf[96];
+    snprintf(buf, sizeof buf, "%s,threads=%d,cap=%d,kMax=%d", sph_pair_mode_name(s->cfg.mode), s->cfg.threads, s->cfg.cap, s->cfg.kMax);
+    return buf;
+}
+
 extern "C" const char* sph_last_error(sph_t* s) { return s ? s->err.c_str() : g_createError.c_str(); }
 
 extern "C" int sph_destroy(sph_t* s)

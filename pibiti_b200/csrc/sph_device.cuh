@@ -85,6 +85,7 @@ void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void*
 enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1 };
 struct SphPairConfig { int mode; int threads; int cap; int kMax; };   // variant, CTA size, staged-candidate capacity, list length
 void sph_pair_default_config(SphPairConfig* cfg);
+const char* sph_pair_mode_name(int mode);
 size_t sph_pair_blocks(const SphPairConfig& cfg, int n);           // CTAs of the pair kernels
 size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n);       // size of the neighbour-list buffer
 cudaError_t sph_pair_prepare(const SphPairConfig& cfg);

@@ -773,6 +773,8 @@ void sph_pair_default_config(SphPairConfig* cfg)
     cfg->mode = SPH_PAIR_L1;  cfg->threads = 128;  cfg->cap = 1344;  cfg->kMax = 48;      // kMax must be a multiple of 4
 }
 
+const char* sph_pair_mode_name(int mode) { return mode == SPH_PAIR_TMA ? "tma" : "l1"; }
+
 size_t sph_pair_blocks(const SphPairConfig& cfg, int n) { return ((size_t)n + cfg.threads - 1) / cfg.threads; }
 
 size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n)

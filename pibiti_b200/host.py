@@ -23,7 +23,8 @@ HOST_ABI_SYMBOLS = (
     "sphh_select_scene", "sphh_add_scene_xml", "sphh_next_scene", "sphh_prev_scene", "sphh_host_arrays",
     "sphh_reset", "sphh_drop", "sphh_emit_id", "sphh_srand", "sphh_update_emitter", "sphh_update",
     "sphh_mark_changed", "sphh_get_array", "sphh_set_array", "sphh_solver", "sphh_load_options",
-    "sphh_save_state", "sphh_load_state",
+    "sphh_save_state", "sphh_load_state", "sphh_set_targets", "sphh_set_emitter", "sphh_cnt_rain", "sphh_changed_flag",
+    "sphh_register_gl", "sphh_pos_buffer", "sphh_timer_fps",
 )
 
 EXTRA_FIELDS = ("initMin", "initMax", "initType", "initLast", "spacing", "fCellSize", "dropR", "rain", "rVel", "r2Vel",
@@ -65,6 +66,13 @@ def _bind():
     L.sphh_load_options.argtypes = [cs, vp]
     L.sphh_save_state.argtypes = [vp, cs]
     L.sphh_load_state.argtypes = [vp, cs]
+    L.sphh_set_targets.argtypes = [vp, vp, vp, vp]
+    L.sphh_set_emitter.argtypes = [vp, ci, vp, vp, C.c_float, ci, ci]
+    L.sphh_cnt_rain.argtypes = [vp]
+    L.sphh_changed_flag.argtypes = [vp, ci]
+    L.sphh_register_gl.argtypes = [vp, C.c_uint, C.c_uint]
+    L.sphh_pos_buffer.argtypes = [vp];     L.sphh_pos_buffer.restype = C.c_uint
+    L.sphh_timer_fps.argtypes = [vp];      L.sphh_timer_fps.restype = C.c_double
     _bound = True
     return L
 
@@ -211,6 +219,21 @@ class CSph:
 
     def UpdateEmitter(self):
         self.L.sphh_update_emitter(self.h)
+
+    def set_targets(self, collider=None, dye=None, acc=None):
+        a = [None if v is None else np.ascontiguousarray(v, np.float32) for v in (collider, dye, acc)]
+        self.L.sphh_set_targets(self.h, *[None if v is None else _p(v) for v in a])
+
+    def set_emitter(self, e: int, pos_lag, rot_lag, vel: float, size: int, size2: int = 0):
+        p, r = np.ascontiguousarray(pos_lag, np.float32), np.ascontiguousarray(rot_lag, np.float32)
+        self.L.sphh_set_emitter(self.h, e, _p(p), _p(r), vel, size, size2)
+
+    @property
+    def cntRain(self) -> int:
+        return self.L.sphh_cnt_rain(self.h)
+
+    def changed_flag(self, clear: bool = False) -> bool:
+        return bool(self.L.sphh_changed_flag(self.h, int(clear)))
 
     def Update(self, nsteps: int = 1):
         rc = self.L.sphh_update(self.h, nsteps)

@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_reset_state", "sph_set_visual", "sph_set_dye", "sph_step", "sph_sync",
     "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
-    "sph_version", "sph_gl_register", "sph_gl_update",
+    "sph_version", "sph_pair_variant", "sph_gl_register", "sph_gl_update",
     "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack", "sph_slab_integrate_pack",
     "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
     "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_force_part", "sph_slab_stats",
@@ -129,6 +129,8 @@ def load() -> C.CDLL:
     lib.sph_last_error.argtypes = [vp]
     lib.sph_last_error.restype = C.c_char_p
     lib.sph_version.restype = C.c_char_p
+    lib.sph_pair_variant.argtypes = [vp]
+    lib.sph_pair_variant.restype = C.c_char_p
     ip = C.POINTER(ci)
     lib.sph_slab_configure.argtypes = [vp, ci, ci, ci, ci]
     lib.sph_slab_set_owned.argtypes = [vp, vp, ci]
@@ -237,6 +239,9 @@ class SphSystem:
         v = C.c_longlong(0)
         self._check(self.lib.sph_kernel_launch_count(self.h, C.byref(v)), "sph_kernel_launch_count")
         return int(v.value)
+
+    def pair_variant(self) -> str:
+        return (self.lib.sph_pair_variant(self.h) or b"").decode()
 
     def stream(self) -> int:
         return int(self.lib.sph_cuda_stream(self.h) or 0)

@@ -37,7 +37,7 @@ MAX_RESET_PARTICLES = 20_000_000
 STEP_SCENES = ["box small default", "Stiff  Dam break", "mini box", "mini dense cells", "mini random",
                "mini cylinder Y", "mini cylinder Z", "mini sphere", "mini wrap Z", "mini cycle Z", "mini waves",
                "mini collider accel", "mini heightmap XZ", "mini heightmap YZ holes", "mini rotor Z", "mini rotor Y",
-               "mini propeller pair"]
+               "mini propeller pair", "mini pump square", "mini pump S"]
 
 
 def vp(a):

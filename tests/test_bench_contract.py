@@ -30,6 +30,10 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the arm times the reference's own code from the reference's own initial state: the product library is not even mapped
+    if cb["kind"] == "reference":
+        assert d["native_so_loaded"] == ["oracle/_ref/libsphref.so"], d["native_so_loaded"]
+        assert d["config"]["initial_state"].startswith("reference scene code")
 
 
 def test_reference_arm_under_torchrun_only_rank_zero_prints():

@@ -187,3 +187,90 @@ def test_checkpoint_roundtrip_host_only(tmp_path):
     assert np.array_equal(p2, pos) and np.array_equal(v2, vel)
     with pytest.raises(Exception):
         t.LoadState(tmp_path / "missing.bin")
+
+
+# ---- the per-step host prologue against the reference's own App::UpdateEmitter -------------
+def _ref_host_lib():
+    import ctypes as C
+    from oracle import oracle as orc
+    if not orc.available("reference"):
+        pytest.skip("oracle/_ref/libsphref.so not built (needs the reference tree at build time)")
+    L = C.CDLL(str(orc.REF_LIB))
+    if not hasattr(L, "refh_update_emitter"):
+        pytest.skip("libsphref.so predates refh_update_emitter: rebuild where the reference tree exists")
+    L.refh_set_emitter.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.refh_set_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+PROLOGUE_SCENES = ["mini emitter rain", "mini rotor Y", "mini propeller pair", "mini waves", "mini collider accel"]
+
+
+@pytest.mark.parametrize("title", PROLOGUE_SCENES)
+def test_update_emitter_matches_the_reference_text(title):
+    """cSPH::UpdateEmitter against App::UpdateEmitter (source/App/Update.cpp:9-97), compiled from the reference
+    tree into oracle/_ref/libsphref.so: 200 steps, bit-for-bit -- SimParams (rotor / wave angles, collider,
+    accelerator and dye lag, dyeClear), the emitter ring index, the rain counter, the dirty flag and every particle
+    slot the emitters and the rain drops write.  Both sides use the C library's rand(): they run one after the other
+    from the same seed."""
+    import ctypes as C
+    from pibiti_b200.lib import SIMPARAMS_DTYPE
+    steps = 200
+    xml_dir = host.DEFAULT_SCENES_XML.parent
+
+    def vp(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def drive(step, setters):
+        """the UI edits both sides receive: collider / dye / accelerator targets move, a second emitter switches on"""
+        set_targets, set_emitter = setters
+        if step == 10:
+            set_targets(np.array([0.03, -0.05, 0.02, 0], np.float32), np.array([0.01, -0.06, 0.0], np.float32),
+                        np.array([-0.02, -0.07, 0.03], np.float32))
+        if step == 60:
+            set_emitter(1, np.array([-0.04, 0.06, 0.02], np.float32), np.array([-35.0, 110.0], np.float32), 1.5, 4, 2)
+        if step == 120:
+            set_targets(np.array([-0.05, -0.09, -0.04, 0], np.float32), None, None)
+
+    def clean(block):
+        out = np.zeros(1, SIMPARAMS_DTYPE)
+        for name in SIMPARAMS_DTYPE.names:
+            out[name] = block[name]
+        out["ff2"] = 0
+        return out.tobytes()
+
+    # -- this repository's host layer
+    s = host.CSph(device=-1)
+    s.select_scene(title)                   # srand(1) + InitScene
+    ours = []
+    for k in range(steps):
+        drive(k, (s.set_targets, s.set_emitter))
+        s.UpdateEmitter()
+        pos, vel = s.host_arrays()
+        ours.append((clean(s.params), s.emitId, s.cntRain, s.changed_flag(clear=(k % 7 == 0)), sha(pos[:, :3]), sha(vel[:, :3])))
+    s.close()
+
+    # -- the reference's text
+    L = _ref_host_lib()
+    import re
+    text = re.sub(r"<!--.*?-->", "", (xml_dir / "Scenes.xml").read_text(errors="replace"), flags=re.S)
+    titles = re.findall(r"<Scene\s+name=\"([^\"]*)\"", text)      # the reference does not read `name` on Linux (Scene_Load.cpp:37-39)
+    L.refh_load(str(xml_dir).encode())
+    L.refh_select_scene(titles.index(title))                       # srand(1) + InitScene
+    L.refh_changed_flag(1)
+    n = s_n = None
+    for k in range(steps):
+        drive(k, (lambda c, d, a: L.refh_set_targets(vp(c), None if d is None else vp(d), None if a is None else vp(a)),
+                  lambda e, p, r, v, sz, sz2: L.refh_set_emitter(e, vp(p), vp(r), v, sz, sz2)))
+        L.refh_update_emitter()
+        par = np.zeros(1, SIMPARAMS_DTYPE)
+        L.refh_live_params(vp(par))
+        n = int(par["numParticles"][0])
+        pos, vel = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+        L.refh_get_host(vp(pos), vp(vel))
+        ref = (clean(par), int(L.refh_emit_id()), int(L.refh_cnt_rain()), bool(L.refh_changed_flag(int(k % 7 == 0))),
+               sha(pos[:, :3]), sha(vel[:, :3]))     # w: the reference leaves vel4.w uninitialised (Update.cpp:76)
+        for name, a, b in zip(("SimParams", "emitId", "cntRain", "bChangedAny", "positions", "velocities"), ours[k], ref):
+            assert a == b, f"{title}: {name} differs from the reference at step {k}"
+    if title == "mini emitter rain":
+        assert L.refh_set_array_calls() > 2 * steps and ours[-1][2] != ours[3][2] or ours[-1][1] != 9   # emitters and rain ran
