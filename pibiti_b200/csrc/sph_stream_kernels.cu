@@ -36,7 +36,19 @@ __device__ __forceinline__ void wall_push(float3& v, float3 n, float diff, float
 struct BoundaryCtx {
     float waveShift;        // rTwist*(1+sinf(rAngle)), evaluated on the host so that it is the same
                             // libm result the CPU oracle sees (System.cu:60)
+    float pumpXs, pumpZs;   // pump outlet box: sinf(angOut*s3)*rad and cosf(angOut*s3)*rad*s4 (System.cu:117-119),
+                            // parameter-only values, from the host's libm for the same reason
 };
+
+inline BoundaryCtx boundary_ctx(const SimParams& par)
+{
+    BoundaryCtx c;
+    c.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
+    const float rad = par.worldMax.x;
+    c.pumpXs = sinf(par.angOut * par.s3) * rad;
+    c.pumpZs = cosf(par.angOut * par.s3) * rad * par.s4;
+    return c;
+}
 
 // Soft penalty boundaries.  pos may be teleported (wrap / cycle / pump exit).
 __device__ __forceinline__ void soft_boundary(const SimParams& par, const BoundaryCtx& ctx, float3& pos, float3& vel)
@@ -115,8 +127,8 @@ __device__ __forceinline__ void soft_boundary(const SimParams& par, const Bounda
         }
         float xs;                                                   // outlet box
         if (ang < 0.5f) {
-            xs = sinf(ang * par.s3) * rad;
-            float zs = cosf(ang * par.s3) * rad * par.s4;
+            xs = ctx.pumpXs;
+            const float zs = ctx.pumpZs;
             if (pos.y > zs) {
                 diff = b - pos.x - xs;
                 if (diff > kBndEps) wall_push(vel, make_float3(1.f, 0.f, 0.f), diff, stiff, dampB, dt);
@@ -684,8 +696,7 @@ void sph_launch_integrate_hash(const SphLaunch& L, const SimParams& par, float4*
                                uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, int first, int count)
 {
     if (count <= 0) return;
-    BoundaryCtx ctx;
-    ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
+    const BoundaryCtx ctx = boundary_ctx(par);
     k_integrate_hash<<<blocks_for(count, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, keyU, rankU, cellCount, first, first + count);
     SPH_COUNT(L);
 }
@@ -696,8 +707,7 @@ void sph_launch_slab_integrate_pack(const SphLaunch& L, const SimParams& par, fl
                                     uint32_t* headDown, uint32_t* headUp)
 {
     if (work <= 0) return;
-    BoundaryCtx ctx;
-    ctx.waveShift = par.rTwist * (1.f + sinf(par.rAngle));
+    const BoundaryCtx ctx = boundary_ctx(par);
     k_slab_integrate_pack<<<blocks_for(work, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, first, count, work, zLo, zHi,
                                                                         hasLower, hasUpper, (SlabRecord*)leavDown, (SlabRecord*)leavUp, capL,
                                                                         (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp);

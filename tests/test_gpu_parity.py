@@ -527,3 +527,143 @@ def test_ragged_particle_counts(oracle_port, n, variant, monkeypatch):
         g.set_array(lib.SPH_VEL, o.get_array(1))
     g.close()
     o.close()
+
+
+# ---- round 2 additions ---------------------------------------------------------------------------------------
+
+def test_particle_count_change_after_a_step_keeps_the_first_particles(oracle_any):
+    """sph_set_params with a smaller numParticles after a step: slots are in sorted order by then, so the library first
+    restores original order; the survivors must be exactly particles [0, m) -- what the reference, which simply runs its
+    kernels over the first numParticles entries, would keep -- and every row of get_array is written.  Growing back
+    re-exposes the old rows once, never a duplicate."""
+    s, g, o, par = start("mini box", oracle_any)
+    g.step(2)
+    o.step(2)
+    pos_full, vel_full = o.get_array(0), o.get_array(1)
+    n, m = g.n, g.n // 2 + 37
+    small = par.copy()
+    small["numParticles"] = m
+    g.set_params(small)
+    g.n = m
+    pg, vg = g.get_array(lib.SPH_POS), g.get_array(lib.SPH_VEL)
+    assert np.array_equal(pg, pos_full[:m]) and np.array_equal(vg, vel_full[:m])
+    o2 = oracle_any.system(small)
+    o2.set_array(0, pos_full[:m])
+    o2.set_array(1, vel_full[:m])
+    g.step(1)
+    o2.step(1)
+    check_integers_exact(g, o2)
+    check_floats(g, o2, small)
+    g.set_params(par)                                       # grow back to the allocation
+    g.n = n
+    ids_pos = g.get_array(lib.SPH_POS)
+    assert np.array_equal(ids_pos[:m], o2.get_array(0)) and np.array_equal(ids_pos[m:], pos_full[m:])
+    o.close()
+    o2.close()
+
+
+@pytest.mark.parametrize("title", ["mini pump square", "mini pump S"])
+def test_pump_boundary_and_exit_teleport(oracle_any, title):
+    """Pump boundary (System.cu:100-158): cylinder frame, outlet box, inlet hole, and the exit -> inlet teleport.
+    Twenty resynchronised steps on the scene as Reset fills it, then particles are put just inside the exit with an
+    outward velocity so that the teleport branch runs: the same particles must jump, to the same place (the inlet
+    position goes through sinf/cosf per particle: 1e-6 of the world size), everything else bit for bit."""
+    s, g, o, par = start(title, oracle_any)
+    for _ in range(20):
+        s.UpdateEmitter()                                   # rotor angle
+        p = s.params
+        g.set_params(p)
+        o.set_params(p)
+        g.step(1)
+        o.step(1)
+        check_integers_exact(g, o)
+        check_floats(g, o, p, REL_LIBM)                     # rotor spheres placed with sinf/cosf
+        g.set_array(lib.SPH_POS, o.get_array(0))
+        g.set_array(lib.SPH_VEL, o.get_array(1))
+    p = s.params
+    pos, vel = o.get_array(0), o.get_array(1)
+    wmax, wmin = p["worldMax"][0], p["worldMin"][0]
+    k = 96
+    rng = np.random.Generator(np.random.PCG64(11))
+    pos[:k, 0] = rng.uniform(-0.02, 0.02, k) if float(p["angOut"][0]) < 0.5 else rng.uniform(0.09, 0.14, k)
+    pos[:k, 1] = wmax[1] - float(p["rDexit"][0]) * rng.uniform(0.1, 0.8, k)
+    pos[:k, 2] = rng.uniform(wmin[2] * 0.8, float(p["hClose"][0]) - 0.01, k)
+    vel[:k, :3] = 0
+    vel[:k, 1] = float(p["rVexit"][0]) + rng.uniform(0.2, 1.0, k)
+    for q in (g, o):
+        q.set_array(0, pos)
+        q.set_array(1, vel)
+    g.step(1)
+    o.step(1)
+    pg, po = g.get_array(lib.SPH_POS), o.get_array(0)
+    jumped_o = np.abs(po[:k, 1] - pos[:k, 1]) > 0.05
+    jumped_g = np.abs(pg[:k, 1] - pos[:k, 1]) > 0.05
+    assert jumped_o.sum() >= k // 2, "the fixture should reach the teleport branch"
+    assert np.array_equal(jumped_o, jumped_g)
+    extent = float(np.abs(p["worldSize"][0]).max())
+    assert np.abs(pg[:, :3] - po[:, :3]).max() <= 1e-6 * extent
+    rest = np.ones(g.n, bool)
+    rest[:k] = False
+    assert np.array_equal(pg[rest], po[rest]), "particles that did not teleport are bit-exact"
+    vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+    assert np.all(np.abs(vg - vo) <= REL_LIBM * max(float(np.abs(vo[:, :3]).max()), 1e-3))
+    o.close()
+
+
+def test_scene_switch_reuses_the_device_buffers(oracle_any):
+    """cSPH::InitScene keeps the solver handle when the next scene fits its buffers (the reference frees and reallocates
+    everything, SPH_Scenes.cpp:9-13): same handle, and a step after the switch still meets the one-step bar."""
+    s = host.CSph(device=0)
+    s.select_scene("box small default")                     # 57K particles: the largest of the three
+    h0 = s.solver().h.value
+    s.Update(3)
+    for title in ("mini waves", "Stiff  Dam break", "mini dense cells"):
+        s.select_scene(title)
+        assert s.solver().h.value == h0, "switching to a smaller scene must not reallocate"
+        par = s.params
+        pos, vel = s.host_arrays()
+        g = s.solver()
+        o = oracle_any.system(par)
+        o.set_array(0, pos)
+        o.set_array(1, vel)
+        assert np.array_equal(g.get_array(lib.SPH_POS), pos)
+        g.step(2)
+        o.step(2)
+        check_integers_exact(g, o)
+        check_floats(g, o, par)
+        o.close()
+    s.select_scene("Extreme box 1 M")                       # does not fit: new buffers
+    assert s.n == 1024 * 1024 and s.solver().h.value is not None
+    s.Update(1)
+    assert np.isfinite(s.getArray(True)).all()
+
+
+def test_checkpoint_resumes_into_an_object_on_another_scene(tmp_path):
+    """The targets the per-step prologue drags the collider and the dye source towards (App::colliderPos / dyePos) travel
+    with the checkpoint: resuming inside an object that sits on a scene with another collider position continues
+    bit-identically."""
+    s = host.CSph(device=0)
+    s.select_scene("mini collider accel")
+    s.set_targets(np.array([0.03, -0.05, 0.02, 0], np.float32), np.array([0.01, -0.06, 0.0], np.float32), None)
+    for _ in range(4):
+        s.UpdateEmitter()
+        s.Update()
+    s.SaveState(tmp_path / "ck.bin")
+    for _ in range(6):
+        s.UpdateEmitter()
+        s.Update()
+    a = (s.getArray(False), s.getArray(True), s.params.tobytes())
+    t = host.CSph(device=0)
+    t.select_scene("mini rotor Z")                          # different collider, rotor on
+    t.Update(2)
+    t.LoadState(tmp_path / "ck.bin")
+    for _ in range(6):
+        t.UpdateEmitter()
+        t.Update()
+    assert np.array_equal(t.getArray(False), a[0]) and np.array_equal(t.getArray(True), a[1]) and t.params.tobytes() == a[2]
+    bad = tmp_path / "bad.bin"
+    raw = bytearray((tmp_path / "ck.bin").read_bytes())
+    raw[16:20] = (12345).to_bytes(4, "little")              # sizeof(Scene) guard
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(Exception):
+        t.LoadState(bad)
