@@ -172,11 +172,12 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1,threads,cap,kMax" -- tuning / test aid
         char mode[8] = {0};  int t = 0, c = 0, k = 0;
         if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024 && k % 4 == 0) {
-            const bool tma = strcmp(mode, "tma") == 0;
-            // the staged variant keeps cap candidates (32 B each in the force kernel) and the list block in shared memory
-            const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : 0;
-            if (smemNeed <= prop.sharedMemPerBlockOptin) {
-                s->cfg.mode = tma ? SPH_PAIR_TMA : SPH_PAIR_L1;
+            const bool tma = strcmp(mode, "tma") == 0, duo = strcmp(mode, "duo") == 0;
+            // staged variant: cap candidates (32 B each in the force kernel) plus the list block in shared memory;
+            // duo variant: k expanded records per thread in shared memory (at least one 32-bit mask word)
+            const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : duo ? (size_t)k * t * 4 + 1024 : 0;
+            if (smemNeed <= prop.sharedMemPerBlockOptin && !(duo && (k < 32 || t > 128))) {
+                s->cfg.mode = tma ? SPH_PAIR_TMA : duo ? SPH_PAIR_DUO : SPH_PAIR_L1;
                 s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
             }
         }
@@ -866,7 +867,7 @@ extern "C" int sph_slab_force_part(sph_t* s, int part)
     if (!b.sorted) return fail(s, SPH_ERR_STATE, "sph_slab_force: call sph_slab_sort first");
     if (part < 0 || part > 2) return SPH_ERR_ARG;
     SphLaunch L = launcher(s);
-    const int T = s->cfg.threads, blocks = (int)sph_pair_blocks(s->cfg, b.count);
+    const int T = sph_pair_particles_per_cta(s->cfg), blocks = (int)sph_pair_blocks(s->cfg, b.count);
     int cLo = 0, cHi = blocks;                  // interior CTAs [cLo, cHi)
     if (s->cfg.mode == SPH_PAIR_TMA) cHi = 0;
     else {

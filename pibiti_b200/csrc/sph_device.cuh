@@ -82,11 +82,14 @@ void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void*
 //   SPH_PAIR_TMA  candidates of a CTA staged in shared memory by TMA bulk copies; neighbour lists hold
 //                 shared-memory slot numbers (uint16).  Both kernels must tile and stage identically.
 //   SPH_PAIR_L1   candidates read through L1 from the sorted arrays; lists hold global sorted indices (uint32).
-enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1 };
+//   SPH_PAIR_DUO  two particles per thread, packed f32x2 arithmetic; the density kernel emits bit-mask neighbour records
+//                 (cap = record words per pair), the force kernel expands them in shared memory (kMax entries per pass).
+enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1, SPH_PAIR_DUO = 2 };
 struct SphPairConfig { int mode; int threads; int cap; int kMax; };   // variant, CTA size, staged-candidate capacity, list length
 void sph_pair_default_config(SphPairConfig* cfg);
 const char* sph_pair_mode_name(int mode);
 size_t sph_pair_blocks(const SphPairConfig& cfg, int n);           // CTAs of the pair kernels
+int sph_pair_particles_per_cta(const SphPairConfig& cfg);
 size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n);       // size of the neighbour-list buffer
 cudaError_t sph_pair_prepare(const SphPairConfig& cfg);
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,

@@ -63,12 +63,14 @@ def check_integers_exact(g, o):
     assert np.array_equal(g.get_array(lib.SPH_POS), o.get_array(0)), "positions, original order"
 
 
-# the two variants of the density/force pair (see pibiti_b200/csrc/sph_device.cuh): "tma,..." stages the
-# candidates in shared memory by TMA bulk copies, "l1,..." reads them through L1.  Format: mode,threads,cap,kMax
-PAIR_VARIANTS = {"l1": "l1,128,1344,48", "tma": "tma,128,1344,48"}
+# the variants of the density/force pair (see pibiti_b200/csrc/sph_device.cuh): "tma,..." stages the candidates in
+# shared memory by TMA bulk copies, "l1,..." reads them through L1 (one particle per thread, index lists), "duo,..." is
+# two particles per thread with packed f32x2 arithmetic and bit-mask neighbour records.  Format: mode,threads,cap,kMax
+# (duo: cap = record words per pair, kMax = expanded records per pass in shared memory)
+PAIR_VARIANTS = {"l1": "l1,128,1344,48", "tma": "tma,128,1344,48", "duo": "duo,128,24,48"}
 
 
-@pytest.mark.parametrize("variant", ["l1", "tma"])
+@pytest.mark.parametrize("variant", ["l1", "tma", "duo"])
 @pytest.mark.parametrize("title", TITLES)
 def test_one_step_parity(oracle_any, golden_steps, title, variant, monkeypatch):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
@@ -140,7 +142,7 @@ def test_colour_and_dye_outputs(oracle_any, clr_type):
     o.close()
 
 
-@pytest.mark.parametrize("variant", ["l1", "tma"])
+@pytest.mark.parametrize("variant", ["l1", "tma", "duo"])
 @pytest.mark.parametrize("title", ["box small default", "Stiff  Dam break", "mini dense cells", "mini waves", "mini wrap Z"])
 def test_trajectory_parity_with_resync(oracle_any, title, variant, monkeypatch):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
@@ -267,10 +269,11 @@ def test_unstaged_fallback_path_matches(oracle_any, monkeypatch):
     o.close()
 
 
-@pytest.mark.parametrize("variant", ["l1", "tma"])
+@pytest.mark.parametrize("variant", ["l1", "tma", "duo"])
 def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch, variant):
     """Lists shorter than the neighbour count make the force kernel take its filtering walk (staged)."""
-    monkeypatch.setenv("SPH_B200_PAIR_CFG", variant + ",128,1536,8")
+    # duo: one record word per pair is never enough -> every pair overflows its stream and the force kernel walks
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", "duo,128,1,32" if variant == "duo" else variant + ",128,1536,8")
     s, g, o, par = start("mini box", oracle_any)
     g.step(1)
     o.step(1)
@@ -279,10 +282,11 @@ def test_neighbour_list_overflow_path_matches(oracle_any, monkeypatch, variant):
     o.close()
 
 
-@pytest.mark.parametrize("cfg", ["tma,64,1024,64", "tma,256,3072,48", "l1,64,16,32", "l1,256,16,64"])
+@pytest.mark.parametrize("cfg", ["tma,64,1024,64", "tma,256,3072,48", "l1,64,16,32", "l1,256,16,64",
+                                 "duo,64,24,64", "duo,32,32,32", "duo,128,12,32"])
 def test_other_cta_shapes_match(oracle_any, monkeypatch, cfg):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", cfg)
-    s, g, o, par = start("Stiff  Dam break", oracle_any)
+    s, g, o, par = start("mini dense cells" if cfg.startswith("duo") else "Stiff  Dam break", oracle_any)
     g.step(1)
     o.step(1)
     check_integers_exact(g, o)
@@ -406,13 +410,15 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     assert np.array_equal(t.getArray(False), a[0]) and np.array_equal(t.getArray(True), a[1])
 
 
+@pytest.mark.parametrize("variant", ["l1", "duo"])
 @pytest.mark.parametrize("lam,ratio,max_par", [(1, 1.0, 16), (3, 1.25, 16), (8, 1.5, 16), (16, 1.25, 16), (16, 1.0, 64)])
-def test_uniform_random_boxes(oracle_any, lam, ratio, max_par):
+def test_uniform_random_boxes(oracle_any, lam, ratio, max_par, variant, monkeypatch):
     """BASELINE config 4: uniform random boxes (documented PCG64 seed) at several occupancies, h/cell ratios and
     maxParInCell: sorted pairs, cell table and neighbour counts bit-exact, density within 1e-5.  lambda = 16 with
     maxParInCell = 16 exercises the truncating walk on about half of the cells."""
     sys.path.insert(0, str(ROOT))
     import bench_sweep
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
     n = 32768
     g, par, pos, vel = bench_sweep.build_system(n, lam, ratio, max_par)
     o = oracle_any.system(par)
@@ -423,6 +429,9 @@ def test_uniform_random_boxes(oracle_any, lam, ratio, max_par):
     check_integers_exact(g, o)
     dg, do = g.dump(lib.DUMP_DENSITY), o.dump(5)
     assert np.all(np.abs(dg - do) <= REL * np.abs(do) + 1e-30)
+    # the pair force on up to ~130 neighbours per particle (no floor on the velocity scale: dt is 1e-7 s here)
+    vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+    assert np.all(np.abs(vg - vo) <= REL * float(np.abs(vo[:, :3]).max()))
     if lam == 16 and max_par == 16:
         assert int(np.bincount(g.dump(lib.DUMP_SORTED_PAIRS)[:, 0]).max()) > 16
     g.close()
@@ -501,7 +510,7 @@ def test_gl_interop_fails_cleanly_without_a_gl_context():
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("variant", ["l1", "tma"])
+@pytest.mark.parametrize("variant", ["l1", "tma", "duo"])
 @pytest.mark.parametrize("n", [1, 37, 1000, 4097])
 def test_ragged_particle_counts(oracle_port, n, variant, monkeypatch):
     """the reference's kernels do not bounds-check and need N to be a multiple of 512; these do, for any N
@@ -538,9 +547,8 @@ def test_particle_count_change_after_a_step_keeps_the_first_particles(oracle_any
     re-exposes the old rows once, never a duplicate."""
     s, g, o, par = start("mini box", oracle_any)
     g.step(2)
-    o.step(2)
-    pos_full, vel_full = o.get_array(0), o.get_array(1)
-    n, m = g.n, g.n // 2 + 37
+    pos_full, vel_full = g.get_array(lib.SPH_POS), g.get_array(lib.SPH_VEL)
+    n, m = g.n, g.n // 2 + 512                             # the reference kernels need a multiple of 512 (SURVEY Q8)
     small = par.copy()
     small["numParticles"] = m
     g.set_params(small)
@@ -627,8 +635,8 @@ def test_scene_switch_reuses_the_device_buffers(oracle_any):
         o.set_array(0, pos)
         o.set_array(1, vel)
         assert np.array_equal(g.get_array(lib.SPH_POS), pos)
-        g.step(2)
-        o.step(2)
+        g.step(1)
+        o.step(1)
         check_integers_exact(g, o)
         check_floats(g, o, par)
         o.close()
