@@ -91,7 +91,7 @@ static const char* check_params(const SimParams* p)
         return "every grid dimension must be >= 4 cells (SURVEY.md Q3: unclamped neighbour hashes must miss)";
     if ((unsigned long long)p->gridSize.x * p->gridSize.y != p->gridSize_yx) return "gridSize_yx != gridSize.y*gridSize.x";
     if ((unsigned long long)p->gridSize_yx * p->gridSize.z != p->numCells) return "numCells != gridSize.x*y*z";
-    if (p->numCells > 0x7fffff00u) return "numCells too large";
+    if (p->numCells > 0x3fffff00u) return "numCells too large";      // the neighbour walk does its hash arithmetic in int32
     return nullptr;
 }
 
@@ -169,15 +169,15 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     } while (0)
 
     sph_pair_default_config(&s->cfg);
-    if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1,threads,cap,kMax" -- tuning / test aid
+    if (const char* env = getenv("SPH_B200_PAIR_CFG")) {     // "tma|l1|rm,threads,cap,kMax" -- tuning / test aid
         char mode[8] = {0};  int t = 0, c = 0, k = 0;
         if (sscanf(env, "%7[a-z0-9],%d,%d,%d", mode, &t, &c, &k) == 4 && t >= 32 && t <= 256 && t % 32 == 0 && c > 0 && c <= 3500 && k > 0 && k <= 1024 && k % 4 == 0) {
-            const bool tma = strcmp(mode, "tma") == 0, duo = strcmp(mode, "duo") == 0;
+            const bool tma = strcmp(mode, "tma") == 0, rm = strcmp(mode, "rm") == 0;
             // staged variant: cap candidates (32 B each in the force kernel) plus the list block in shared memory;
-            // duo variant: k expanded records per thread in shared memory (at least one 32-bit mask word)
-            const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : duo ? (size_t)k * t * 4 + 1024 : 0;
-            if (smemNeed <= prop.sharedMemPerBlockOptin && !(duo && (k < 32 || t > 128))) {
-                s->cfg.mode = tma ? SPH_PAIR_TMA : duo ? SPH_PAIR_DUO : SPH_PAIR_L1;
+            // rm variant: cap = records per particle (kMax unused)
+            const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : 0;
+            if (smemNeed <= prop.sharedMemPerBlockOptin && !(rm && c > 64)) {
+                s->cfg.mode = tma ? SPH_PAIR_TMA : rm ? SPH_PAIR_RM : SPH_PAIR_L1;
                 s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
             }
         }

@@ -77,14 +77,46 @@ void sph_launch_slab_hash_hist(const SphLaunch& L, const SimParams& par, const f
 void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void* inAbove, const void* ownDown, const void* ownUp,
                             int capL, int capB, float4* pos, float4* vel, uint32_t* idx, int work0, int capacity, uint32_t* dev);
 
+// slab mode with device-resident bookkeeping (multi-GPU driver): words of the handle's `counters` array
+enum SlabDevWord {
+    SD_WORK = 4,        // work-set size (owned + appended arrivals + ghosts + retired slots)
+    SD_OVERFLOW = 5,    // a message section or the work set was too small
+    SD_LOST = 6,        // an owned particle left the owned layers without being handed over (moved > 1 layer in a step)
+    SD_WORK0 = 7,       // work-set size before the arrivals of this step were appended
+    SD_FIRST = 8,       // sorted ranges after the sort: owned = [SD_FIRST, SD_END) ...
+    SD_END = 9,
+    SD_BLO = 10,        // ... first owned layer = [SD_FIRST, SD_BLO), last owned layer = [SD_BHI, SD_END)
+    SD_BHI = 11,
+    SD_G2 = 12,         // ghosts above = [SD_END, SD_G2); ghosts below = [0, SD_FIRST)
+    SD_DPERR = 13,      // rho,p rows received != ghosts expected
+    SD_WORDS = 16
+};
+void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                             uint32_t* st, int zLo, int zHi, int hasLower, int hasUpper,
+                                             void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
+                                             uint32_t* headDown, uint32_t* headUp);
+void sph_launch_slab_interior_hist(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                   uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, uint32_t* st, int bound,
+                                   long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi,
+                                   uint32_t* keyMaxSlots, int split);
+void sph_launch_slab_unpack_hist(const SphLaunch& L, const SimParams& par, const void* inBelow, const void* inAbove,
+                                 const void* ownDown, const void* ownUp, int capL, int capB, float4* pos, float4* vel, uint32_t* idx,
+                                 int capacity, uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, uint32_t* st,
+                                 long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi, uint32_t* keyMaxSlots);
+void sph_launch_slab_scan_bound(const SphLaunch& L, uint32_t* keyMaxSlots, uint32_t guardCells, int numCellsLocal);
+void sph_launch_slab_bounds(const SphLaunch& L, const uint32_t* cellStart, const uint32_t* scanBound, uint32_t* st,
+                            const int cells[5], int hasLower, int hasUpper);
+void sph_launch_slab_pack_dp(const SphLaunch& L, const float4* posP, const float4* velD, uint32_t* st, float4* dpDown, float4* dpUp, int capRows);
+void sph_launch_slab_unpack_dp(const SphLaunch& L, const float4* dpBelow, const float4* dpAbove, uint32_t* st, float4* posP, float4* velD, int capRows);
+
 // ---- sph_pair_kernels.cu ----------------------------------------------------------------------
 // Two variants of the density/force pair, same results:
 //   SPH_PAIR_TMA  candidates of a CTA staged in shared memory by TMA bulk copies; neighbour lists hold
 //                 shared-memory slot numbers (uint16).  Both kernels must tile and stage identically.
 //   SPH_PAIR_L1   candidates read through L1 from the sorted arrays; lists hold global sorted indices (uint32).
-//   SPH_PAIR_DUO  two particles per thread, packed f32x2 arithmetic; the density kernel emits bit-mask neighbour records
-//                 (cap = record words per pair), the force kernel expands them in shared memory (kMax entries per pass).
-enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1, SPH_PAIR_DUO = 2 };
+//   SPH_PAIR_RM   like L1, but the hits travel as {32-candidate bit mask, first sorted index} records (cap = records per
+//                 particle): no per-neighbour stores in the density kernel, no cap on the number of neighbours.
+enum SphPairMode { SPH_PAIR_TMA = 0, SPH_PAIR_L1 = 1, SPH_PAIR_RM = 2 };
 struct SphPairConfig { int mode; int threads; int cap; int kMax; };   // variant, CTA size, staged-candidate capacity, list length
 void sph_pair_default_config(SphPairConfig* cfg);
 const char* sph_pair_mode_name(int mode);
@@ -95,17 +127,19 @@ cudaError_t sph_pair_prepare(const SphPairConfig& cfg);
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count);
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count,
+                        const uint32_t* dev = nullptr /* slab mode: {first, end, ...} read on the device; count = launch bound */);
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
                       const uint32_t* ctaRows, float4* velOut, int first, int count,
-                      int ctaFirst = 0, int ctaCount = -1 /* L1 variant: only CTAs [ctaFirst, ctaFirst+ctaCount) of the range */);
+                      int ctaFirst = 0, int ctaCount = -1 /* L1 / rm variants: only CTAs [ctaFirst, ctaFirst+ctaCount) of the range */,
+                      const uint32_t* dev = nullptr, int part = 0 /* with dev: 1 = CTAs without ghost neighbours, 2 = the others */);
 
 // ---- sph_extras_kernels.cu --------------------------------------------------------------------
 bool sph_needs_obstacles(const SimParams& par);        // height map or rotor configured
 void sph_launch_obstacles(const SphLaunch& L, const SimParams& par, const float4* posP, const float4* velD, float4* velNew,
-                          int first, int count);
+                          int first, int count, const uint32_t* dev = nullptr);
 void sph_launch_color_dye(const SphLaunch& L, const SimParams& par, const float4* posS, const float4* velS, const float4* velD,
                           const float4* velNew, const uint32_t* keyS, const uint32_t* cellStart, const uint32_t* idx,
                           float4* clr, float* dye, int first, int count);

@@ -29,8 +29,9 @@ __device__ __forceinline__ void add3(float3& a, float3 b) { a.x += b.x;  a.y += 
 
 __global__ void __launch_bounds__(128)
 k_obstacles(const __grid_constant__ SimParams par, const float4* __restrict__ posP, const float4* __restrict__ velD,
-            float4* __restrict__ velNew, int first, int n)
+            float4* __restrict__ velNew, int first, int n, const uint32_t* __restrict__ dev)
 {
+    if (dev) { first = (int)__ldg(dev);  n = (int)__ldg(dev + 1); }
     const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 pp = posP[i];
@@ -228,10 +229,10 @@ k_color_dye(const __grid_constant__ SimParams par, const float4* __restrict__ po
 bool sph_needs_obstacles(const SimParams& par) { return par.iHmap > 0 || par.rotType > 0; }
 
 void sph_launch_obstacles(const SphLaunch& L, const SimParams& par, const float4* posP, const float4* velD, float4* velNew,
-                          int first, int count)
+                          int first, int count, const uint32_t* dev)
 {
     if (count <= 0) return;
-    k_obstacles<<<(count + 127) / 128, 128, 0, L.stream>>>(par, posP, velD, velNew, first, first + count);
+    k_obstacles<<<(count + 127) / 128, 128, 0, L.stream>>>(par, posP, velD, velNew, first, first + count, dev);
     SPH_COUNT(L);
 }
 

@@ -29,6 +29,7 @@
 #include "sph_device.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace {
 
@@ -592,6 +593,17 @@ k_force(const __grid_constant__ SimParams par, int cap, int kMax,
     velOut[i] = finish_velocity(par, pp, vd, velW, f);
 }
 
+// Slab mode with device-resident ranges: dev = {first owned, end of owned, end of the first owned layer, start of the last
+// owned layer}.  part 1 = CTAs whose particles all lie strictly between the two boundary layers (no ghost neighbours),
+// part 2 = the others, part 0 = all.
+__device__ __forceinline__ bool pair_cta_in_part(int p0, int perCta, int n, const uint32_t* __restrict__ dev, int part)
+{
+    if (part == 0) return true;
+    const int p1 = min(n, p0 + perCta);
+    const bool interior = p0 >= (int)__ldg(dev + 2) && p1 <= (int)__ldg(dev + 3);
+    return part == 1 ? interior : !interior;
+}
+
 // ---- L1-cached variant ------------------------------------------------------------------------------
 // Same walk and same arithmetic, but candidates are read straight from the sorted arrays through L1
 // (LDG.128 on the read-only path) instead of being staged by TMA: no shared memory, no CTA prologue,
@@ -613,9 +625,10 @@ k_density_l1(const __grid_constant__ SimParams par, int kMax,
              const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
              const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
              float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
-             uint32_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int first, int n)
+             uint32_t* __restrict__ nlist, uint16_t* __restrict__ ncount, int first, int n, const uint32_t* __restrict__ dev)
 {
     const int T = blockDim.x;
+    if (dev) { first = (int)__ldg(dev);  n = (int)__ldg(dev + 1); }      // slab mode: the owned range lives on the device
     const int i = first + blockIdx.x * T + threadIdx.x;
     if (i >= n) return;
     const float4 p4 = posS[i];
@@ -708,11 +721,15 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
            const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
            const uint32_t* __restrict__ nlist, const uint16_t* __restrict__ ncount,
-           float4* __restrict__ velOut, int first, int n, int ctaFirst)
+           float4* __restrict__ velOut, int first, int n, int ctaFirst, const uint32_t* __restrict__ dev, int part)
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
     const int cta = blockIdx.x + ctaFirst;     // a launch may cover a sub-range of the CTAs the density launch used
+    if (dev) {
+        first = (int)__ldg(dev);  n = (int)__ldg(dev + 1);
+        if (!pair_cta_in_part(first + cta * T, T, n, dev, part)) return;
+    }
     const int i = first + cta * T + threadIdx.x;
     if (i >= n) return;
     const float4 pp = posP[i];
@@ -762,355 +779,217 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
 }
 
 
-// ---- "duo" variant: two particles per thread, packed f32x2 arithmetic, bit-mask neighbour records ----------------
-// A thread owns TWO consecutive sorted particles (they sit in the same cell or in adjacent cells, so their candidate
-// ranges coincide or overlap) and tests every candidate it loads against both: one LDG.128 per two pair tests, and the
-// whole distance / kernel evaluation runs on the packed f32x2 pipe (FADD2 / FMUL2 / FFMA2 with the candidate coordinate
-// as a scalar-broadcast operand), which is the only way to reach the full FP32 rate on sm_100.
-//
-// Exactness.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, so the packed r2 is written with explicit fused
-// multiply-adds; it differs from the CPU's unfused (x*x + y*y) + z*z by at most 6 * 2^-24 * r2.  The decision r2 < h2
-// is taken from the fused value whenever |h2 - r2| >= 2^-19 * h2 (five times that bound); a 32-candidate word in which
-// any test falls inside the band is re-evaluated with the unfused arithmetic of dist2_exact.  The neighbour SET is
-// therefore bit-identical to the oracle's; only the summed weights differ, by ~1e-7 relative.
-//
-// Neighbour records.  Instead of one 4-byte index per hit (about 100 B per particle written by the density kernel and
-// read back by the force kernel), the density kernel keeps the hits of 32 consecutive candidates as one bit mask per
-// particle and emits, per pair, a stream of 16-byte words {first sorted index, mask of particle 0, mask of particle 1}
-// -- about ten words per pair -- in registers, with one coalesced store per word.  The force kernel expands the words of
-// its pair into a per-thread column of shared memory (union of the two masks, two flag bits per entry) and then runs a
-// uniform loop over it: every neighbour record is gathered once for both particles.
-typedef unsigned long long f32x2;
+// ---- row-mask variant ("rm") -----------------------------------------------------------------------
+// One thread per sorted particle, candidates through L1 like the L1 variant, but the hits are not written as one index
+// per neighbour.  The density kernel keeps the hits of up to 32 consecutive candidates as a bit mask in a register and
+// emits one 8-byte record {mask, first sorted index} per non-empty word: nine coalesced 8-byte stores per particle
+// instead of ~25 scattered 4-byte stores (ncu, profiles/: the index-list stores were 40 % of the density kernel's L1
+// wavefronts and 1.1 GB of DRAM writes per step at 8M).  The force kernel walks the records of its particle with a
+// cursor (lowest set bit first, so neighbours are visited in the candidate order of the reference) and prefetches the
+// next record; only the refill is divergent.  There is no cap on the number of NEIGHBOURS any more, only on the number of
+// records (cap; dense cells need one record per 32 candidates of a row), so dense scenes keep their lists.
+constexpr uint32_t kRmInvalid = 0xFFFFu;       // nrec value: the record stream overflowed, the force kernel walks
 
-__device__ __forceinline__ f32x2 dup2(float v) { return pack_f32x2(v, v); }           // folds into a scalar-broadcast operand
-__device__ __forceinline__ void unpack_f32x2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d;  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));  return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d;  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));  return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d;  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));  return d; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d;  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));  return d; }
-__device__ __forceinline__ float min3_abs(float m, float a, float b)
-{
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));       // FMNMX3 with |.| modifiers
-    return r;
-}
-
-constexpr uint32_t kDuoInvalid = 0xFFFFu;      // nwords value: the pair's record stream overflowed, the force kernel walks
-constexpr uint32_t kDuoFlag0 = 1u << 30, kDuoFlag1 = 1u << 31, kDuoIndexMask = kDuoFlag0 - 1u;
-
-// the two particles of a thread, packed lane 0 / lane 1
-struct DuoCentres { f32x2 px, py, pz; };
-
-// One word = candidates [g0, g1), at most 32, bit k of the masks = candidate g0 + k.  Particle 0 sees candidates below e0,
-// particle 1 candidates from a1 on (their 3-cell windows inside the common range).  Fused packed evaluation; `mn` collects
-// the smallest |h2 - r2| for the exactness check.
-template <bool SELF>
-__device__ __forceinline__ void duo_density_word(const float4* __restrict__ posS, uint32_t g0, uint32_t g1, uint32_t e0, uint32_t a1,
-                                                 uint32_t i0, uint32_t i1, const DuoCentres& C, f32x2 hh,
-                                                 float& s0, float& s1, uint32_t& m0, uint32_t& m1, float& mn)
-{
-    uint32_t bit = 1u;
-    #pragma unroll 4
-    for (uint32_t g = g0; g < g1; g++, bit += bit) {
-        const float4 q = __ldg(posS + g);
-        const f32x2 dx = sub2(C.px, dup2(q.x)), dy = sub2(C.py, dup2(q.y)), dz = sub2(C.pz, dup2(q.z));
-        const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-        const f32x2 c = sub2(hh, r2), cc = mul2(c, c);
-        float ca, cb, cca, ccb;
-        unpack_f32x2(c, ca, cb);  unpack_f32x2(cc, cca, ccb);
-        mn = min3_abs(mn, ca, cb);
-        bool h0 = ca > 0.f && g < e0, h1 = cb > 0.f && g >= a1;
-        if (SELF) { h0 = h0 && g != i0;  h1 = h1 && g != i1; }
-        s0 = h0 ? fmaf(cca, ca, s0) : s0;
-        s1 = h1 ? fmaf(ccb, cb, s1) : s1;
-        m0 |= h0 ? bit : 0u;
-        m1 |= h1 ? bit : 0u;
-    }
-}
-
-// the same word with the CPU's unfused arithmetic: only the masks are recomputed (a test inside the band contributes
-// less than (2^-19 h2)^3 to the sum either way).  Everything travels by value: a reference parameter of a function that
-// is not inlined would pin the caller's accumulators in local memory.
-__device__ __noinline__ uint2 duo_density_word_exact(const float4* __restrict__ posS, uint32_t g0, uint32_t g1, uint32_t e0, uint32_t a1,
-                                                     uint32_t i0, uint32_t i1, float3 c0, float3 c1, float h2)
-{
-    uint32_t bit = 1u, m0 = 0u, m1 = 0u;
-    for (uint32_t g = g0; g < g1; g++, bit += bit) {
-        const float4 q = __ldg(posS + g);
-        const bool h0 = dist2_exact(c0.x - q.x, c0.y - q.y, c0.z - q.z) < h2 && g < e0 && g != i0;
-        const bool h1 = dist2_exact(c1.x - q.x, c1.y - q.y, c1.z - q.z) < h2 && g >= a1 && g != i1;
-        m0 |= h0 ? bit : 0u;
-        m1 |= h1 ? bit : 0u;
-    }
-    return make_uint2(m0, m1);
-}
-
-// this thread's column of the CTA's record block: word w at col[w * stride]; words past `cap` are counted, not stored
-struct DuoEmit { uint4* col;  uint32_t stride, cap; };
-
-__device__ __forceinline__ uint32_t duo_put(const DuoEmit& out, uint32_t w, uint32_t base, uint32_t m0, uint32_t m1)
-{
-    if ((m0 | m1) == 0u) return w;
-    if (w < out.cap) out.col[(size_t)w * out.stride] = make_uint4(base, m0, m1, 0u);
-    return w + 1u;
-}
-
-// A row that contains a cell with more than maxParInCell entries: candidates beyond the first maxParInCell
-// of their cell are not visited.  Rare, so plain scalar code over the cells [cLo, cHi]; record words stay relative to the
-// first candidate of the row.  Accumulators in and out by value.
-struct DuoRowResult { float s0, s1;  uint32_t n0, n1, w; };
-
-__device__ __noinline__ DuoRowResult duo_density_row_truncated(const float4* __restrict__ posS, const uint32_t* __restrict__ cellStart,
-                                                               long long cLo, long long cHi, uint32_t maxPar, uint32_t e0, uint32_t a1,
-                                                               uint32_t i0, uint32_t i1, float3 c0, float3 c1, float h2,
-                                                               DuoEmit out, DuoRowResult acc)
-{
-    uint32_t base = __ldg(cellStart + cLo), m0 = 0u, m1 = 0u;
-    for (long long c = cLo; c <= cHi; c++) {
-        const uint32_t cs = __ldg(cellStart + c), ce = __ldg(cellStart + c + 1), lim = min(ce, cs + maxPar);
-        for (uint32_t g = cs; g < lim; g++) {
-            while (g - base >= 32u) {
-                acc.w = duo_put(out, acc.w, base, m0, m1);  acc.n0 += __popc(m0);  acc.n1 += __popc(m1);
-                m0 = m1 = 0u;  base += 32u;
-            }
-            const float4 q = __ldg(posS + g);
-            const float r0 = dist2_exact(c0.x - q.x, c0.y - q.y, c0.z - q.z), r1 = dist2_exact(c1.x - q.x, c1.y - q.y, c1.z - q.z);
-            const uint32_t bit = 1u << (g - base);
-            if (r0 < h2 && g < e0 && g != i0) { const float cc = h2 - r0;  acc.s0 += cc * cc * cc;  m0 |= bit; }
-            if (r1 < h2 && g >= a1 && g != i1) { const float cc = h2 - r1;  acc.s1 += cc * cc * cc;  m1 |= bit; }
-        }
-    }
-    acc.w = duo_put(out, acc.w, base, m0, m1);  acc.n0 += __popc(m0);  acc.n1 += __popc(m1);
-    return acc;
-}
-
-// MINB = resident CTAs per SM the register allocation aims at: 10 (48 registers, a few values of the row loop spill to
-// local memory), 9 (56 registers) or 8 (64 registers); measured on the B200, see profiles/
-template <int MINB>
+// MINB = resident 128-thread CTAs per SM the register allocation aims at: 12 (40 registers) or 16 (32, a few spills)
+template <int MINB, int UNROLL>
 __global__ void __launch_bounds__(128, MINB)
-k_density_duo(const __grid_constant__ SimParams par, int wordCap,
-              const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
-              const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
-              float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
-              uint4* __restrict__ records, uint16_t* __restrict__ nwords, int first, int n)
+k_density_rm(const __grid_constant__ SimParams par, int recCap,
+             const float4* __restrict__ posS, const float4* __restrict__ velS, const uint32_t* __restrict__ keyS,
+             const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+             float4* __restrict__ posP, float4* __restrict__ velD, uint32_t* __restrict__ neighborCounts,
+             uint2* __restrict__ records, uint16_t* __restrict__ nrec, int first, int n, const uint32_t* __restrict__ dev)
 {
-    const int T = blockDim.x;
-    const int pairIdx = blockIdx.x * T + threadIdx.x;
-    const int i0 = first + 2 * pairIdx;
-    if (i0 >= n) return;
-    const bool single = i0 + 1 >= n;
-    const int i1 = single ? i0 : i0 + 1;
-    const float4 p0 = posS[i0], p1 = posS[i1];
-    const long long key0 = keyS[i0], key1 = keyS[i1];
+    if (dev) { first = (int)__ldg(dev);  n = (int)__ldg(dev + 1); }      // slab mode: the owned range lives on the device
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p4 = posS[i];
+    const int key = (int)keyS[i];
     const bool trunc = __ldg(maxCount) > par.maxParInCell;
-    const long long C = par.numCells;
-    const float h2 = par.h2, tau = h2 * 1.9073486328125e-6f;      // 2^-19 h2
-    const f32x2 hh = dup2(h2);
-    DuoCentres ctr;
-    ctr.px = pack_f32x2(p0.x, p1.x);  ctr.py = pack_f32x2(p0.y, p1.y);  ctr.pz = pack_f32x2(p0.z, p1.z);
-    const float3 c0 = make_float3(p0.x, p0.y, p0.z), c1 = make_float3(p1.x, p1.y, p1.z);
-    const uint32_t self0 = (uint32_t)i0, self1 = single ? 0xFFFFFFFFu : (uint32_t)i1;
+    const float h2 = par.h2;
+    const int C = (int)par.numCells;                                      // sph_create keeps numCells below 2^30
+    const unsigned long long pxy = pack_f32x2(p4.x, p4.y);
+    const float pz = p4.z;
 
-    DuoEmit out;
-    out.col = records + (size_t)blockIdx.x * wordCap * T + threadIdx.x;
-    out.stride = (uint32_t)T;  out.cap = (uint32_t)wordCap;
-
-    float s0 = 0.f, s1 = 0.f;
-    uint32_t n0 = 0u, n1 = 0u, w = 0u;
-    // cells no more than two apart share one walk over the union of their rows; otherwise (a gap in the fluid, the end of
-    // a grid row) each particle walks alone
-    const bool joint = !single && key1 - key0 <= 2;
-    const int passes = (single || joint) ? 1 : 2;
-    #pragma unroll 1
-    for (int pass = 0; pass < passes; pass++) {
-        const bool en0 = joint || pass == 0, en1 = !single && (joint || pass == 1);
-        const long long kL = en0 ? key0 : key1, kH = en1 ? key1 : key0;
-        const int span = (int)(kH - kL);            // 0, 1 or 2: the row covers span + 3 cells
+    float sum = 0.f;
+    uint32_t w = 0u, cnt = 0u;
+    // this thread's column of the CTA's record block [record][thread]; advances one row per record
+    uint2* rec = records + (size_t)blockIdx.x * recCap * blockDim.x + threadIdx.x;
+    // window [a, e): one record per 32 candidates; bit k of the mask = candidate base + k.  centre = the centre row,
+    // where the walk steps over the particle itself (Kernel_Cell.cui:166).  The tail of a candidate is predicated
+    // instructions from one PTX block (hit test, c^3 into the sum, bit into the mask): no branch, no select.
+    auto window = [&](uint32_t a, uint32_t e, auto centreTag) {
+        constexpr bool centre = decltype(centreTag)::value;
+        for (uint32_t base = a; base < e; base += 32u) {
+            const uint32_t g1 = min(e, base + 32u);
+            uint32_t mask = 0u, bit = 1u;
+            #pragma unroll (UNROLL)
+            for (uint32_t g = base; g < g1; g++, bit += bit) {
+                const float4 q = __ldg(posS + g);
+                const float r2 = dist2_exact_packed(pxy, pz, q);
+                const float c = __fsub_rn(h2, r2);
+                const float cc = c * c;
+                if (centre)
+                    asm("{ .reg .pred h;  setp.lt.f32 h, %2, %3;  setp.ne.and.u32 h, %7, %8, h;\n"
+                        "  @h fma.rn.f32 %0, %4, %5, %0;  @h or.b32 %1, %1, %6; }"
+                        : "+f"(sum), "+r"(mask) : "f"(r2), "f"(h2), "f"(cc), "f"(c), "r"(bit), "r"(g), "r"((uint32_t)i));
+                else
+                    asm("{ .reg .pred h;  setp.lt.f32 h, %2, %3;\n"
+                        "  @h fma.rn.f32 %0, %4, %5, %0;  @h or.b32 %1, %1, %6; }"
+                        : "+f"(sum), "+r"(mask) : "f"(r2), "f"(h2), "f"(cc), "f"(c), "r"(bit));
+            }
+            if (mask != 0u) {
+                if (w < (uint32_t)recCap) *rec = make_uint2(mask, base);
+                rec += blockDim.x;
+                w++;
+                cnt += __popc(mask);
+            }
+        }
+    };
+    auto row = [&](uint32_t a, uint32_t e, int r) {
+        if (r == 4) window(a, e, std::true_type{});  else window(a, e, std::false_type{});
+    };
+    // hash of the centre cell of row r: rows advance by one y line, every third row by one z plane (32-bit arithmetic)
+    const int gx = (int)par.gridSize.x, gyx = (int)par.gridSize_yx;
+    int hb = key - gyx - gx;
+    if (!trunc) {
+        // sorted-index bounds of the three cells around hb, clipped to the grid; the next row's are in flight
+        auto bounds = [&](int h, uint32_t& a, uint32_t& e) -> bool {
+            const int lo = max(h - 1, 0), hi = min(h + 1, C - 1);
+            if (lo > hi) { a = e = 0u;  return false; }
+            a = __ldg(cellStart + lo);  e = __ldg(cellStart + hi + 1);
+            return true;
+        };
+        uint32_t a, e, an = 0, en = 0;
+        bool ok = bounds(hb, a, e), okn = false;
         #pragma unroll 1
         for (int r = 0; r < kRows; r++) {
-            const long long hb = kL + row_hash(par, 0u, r);            // cell of the lower particle in this row
-            long long lo = hb - 1, hi = hb + span + 1;
-            if (lo < 0) lo = 0;
-            if (hi > C - 1) hi = C - 1;
-            if (lo > hi) continue;
-            // cell-table entries of the row: b[k] = cellStart[lo + k], k = 0 .. cells (at most six)
-            const int cells = (int)(hi - lo) + 1;
-            uint32_t b0 = __ldg(cellStart + lo), b1 = __ldg(cellStart + lo + 1), b2 = b1, b3 = b1, b4 = b1, b5 = b1;
-            if (cells > 1) b2 = __ldg(cellStart + lo + 2);
-            if (cells > 2) b3 = __ldg(cellStart + lo + 3);
-            if (cells > 3) b4 = __ldg(cellStart + lo + 4);
-            if (cells > 4) b5 = __ldg(cellStart + lo + 5);
-            if (cells < 2) b2 = b1;
-            if (cells < 3) b3 = b2;
-            if (cells < 4) b4 = b3;
-            if (cells < 5) b5 = b4;
-            const uint32_t aU = b0, eU = b5;
-            if (aU == eU) continue;
-            // windows of the two particles inside [aU, eU): particle 0 owns cells hb-1..hb+1, particle 1 cells hb+span-1..hb+span+1
-            auto entry = [&](long long c) -> uint32_t {               // cellStart[c] for lo <= c <= hi + 1, from the registers
-                const int k = (int)(c - lo);
-                return k <= 0 ? b0 : k == 1 ? b1 : k == 2 ? b2 : k == 3 ? b3 : k == 4 ? b4 : b5;
-            };
-            uint32_t e0 = 0u, a1 = 0xFFFFFFFFu;
-            if (en0 && hb + 1 >= 0) e0 = entry(min(hb + 1, C - 1) + 1);
-            if (en1 && hb + span - 1 <= C - 1) a1 = entry(max(hb + span - 1, 0LL));
-            if (trunc) {
-                const uint32_t mp = par.maxParInCell;
-                if (b1 - b0 > mp || b2 - b1 > mp || b3 - b2 > mp || b4 - b3 > mp || b5 - b4 > mp) {
-                    DuoRowResult acc;
-                    acc.s0 = s0;  acc.s1 = s1;  acc.n0 = n0;  acc.n1 = n1;  acc.w = w;
-                    acc = duo_density_row_truncated(posS, cellStart, lo, hi, mp, e0, a1, self0, self1, c0, c1, h2, out, acc);
-                    s0 = acc.s0;  s1 = acc.s1;  n0 = acc.n0;  n1 = acc.n1;  w = acc.w;
-                    continue;
+            hb += (r % 3 == 2) ? gyx - 2 * gx : gx;
+            if (r + 1 < kRows) okn = bounds(hb, an, en);
+            if (ok) row(a, e, r);
+            a = an;  e = en;  ok = okn;
+        }
+    } else {
+        // some cell holds more than maxParInCell particles: a row is still one run unless one of ITS cells overflows
+        const uint32_t mp = par.maxParInCell;
+        #pragma unroll 1
+        for (int r = 0; r < kRows; r++) {
+            const RowCells cur = load_row_cells(cellStart, (long long)hb, (long long)C);
+            hb += (r % 3 == 2) ? gyx - 2 * gx : gx;
+            if (cur.ncell == 0) continue;
+            const bool over = cur.b1 - cur.b0 > mp || (cur.ncell > 1 && cur.b2 - cur.b1 > mp) || (cur.ncell > 2 && cur.b3 - cur.b2 > mp);
+            if (!over) {
+                row(cur.b0, cur.ncell == 3 ? cur.b3 : cur.ncell == 2 ? cur.b2 : cur.b1, r);
+            } else {
+                #pragma unroll 1
+                for (int x = 0; x < cur.ncell; x++) {
+                    const uint32_t c0 = x == 0 ? cur.b0 : x == 1 ? cur.b1 : cur.b2, c1 = x == 0 ? cur.b1 : x == 1 ? cur.b2 : cur.b3;
+                    row(c0, min(c1, c0 + mp), r);
                 }
-            }
-            for (uint32_t base = aU; base < eU; base += 32u) {
-                const uint32_t gEnd = min(eU, base + 32u);
-                uint32_t m0 = 0u, m1 = 0u;
-                float mn = 1e30f;
-                if (r == 4) duo_density_word<true>(posS, base, gEnd, e0, a1, self0, self1, ctr, hh, s0, s1, m0, m1, mn);
-                else        duo_density_word<false>(posS, base, gEnd, e0, a1, 0u, 0u, ctr, hh, s0, s1, m0, m1, mn);
-                if (mn < tau) {
-                    const uint2 mm = duo_density_word_exact(posS, base, gEnd, e0, a1, r == 4 ? self0 : 0xFFFFFFFFu,
-                                                            r == 4 ? self1 : 0xFFFFFFFFu, c0, c1, h2);
-                    m0 = mm.x;  m1 = mm.y;
-                }
-                n0 += __popc(m0);  n1 += __popc(m1);
-                w = duo_put(out, w, base, m0, m1);
             }
         }
     }
-
-    const float4 v0 = velS[i0];
-    const float d0 = s0 * par.Poly6Kern * par.particleMass;               // Kernel_Cell.cui:194-195
-    posP[i0] = make_float4(p0.x, p0.y, p0.z, (d0 - par.restDensity) * par.stiffness);
-    velD[i0] = make_float4(v0.x, v0.y, v0.z, d0);
-    if (neighborCounts) neighborCounts[i0] = n0;
-    if (!single) {
-        const float4 v1 = velS[i1];
-        const float d1 = s1 * par.Poly6Kern * par.particleMass;
-        posP[i1] = make_float4(p1.x, p1.y, p1.z, (d1 - par.restDensity) * par.stiffness);
-        velD[i1] = make_float4(v1.x, v1.y, v1.z, d1);
-        if (neighborCounts) neighborCounts[i1] = n1;
-    }
-    nwords[i0 >> 1] = w <= (uint32_t)wordCap ? (uint16_t)w : (uint16_t)kDuoInvalid;
+    const float dens = sum * par.Poly6Kern * par.particleMass;            // Kernel_Cell.cui:194-195
+    const float pres = (dens - par.restDensity) * par.stiffness;
+    const float4 v4 = velS[i];                  // not needed before: keeping it live across the walk costs registers
+    posP[i] = make_float4(p4.x, p4.y, p4.z, pres);
+    velD[i] = make_float4(v4.x, v4.y, v4.z, dens);
+    nrec[i] = w <= (uint32_t)recCap ? (uint16_t)w : (uint16_t)kRmInvalid;
+    if (neighborCounts) neighborCounts[i] = cnt;
 }
 
-// one neighbour record against both particles of the thread (compForcePair, Kernel_Cell.cui:210-228, packed)
-struct DuoForceState { f32x2 px, py, pz, vx, vy, vz, pres, dens, fx, fy, fz; };
-
-__device__ __forceinline__ void force_pair_duo(float4 q, float4 u, uint32_t entry, DuoForceState& S, const ForceConsts& k)
+// records are read once: around L1, so that they do not evict the gathered particle rows
+__device__ __forceinline__ uint2 load_record(const uint2* p)
 {
-    const f32x2 dx = sub2(S.px, dup2(q.x)), dy = sub2(S.py, dup2(q.y)), dz = sub2(S.pz, dup2(q.z));
-    const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-    float r2a, r2b;
-    unpack_f32x2(r2, r2a, r2b);
-    const float inva = rsqrtf(r2a), invb = rsqrtf(r2b);
-    float ra, rb;
-    unpack_f32x2(mul2(r2, pack_f32x2(inva, invb)), ra, rb);
-    ra = fmaxf(k.minDist, ra);  rb = fmaxf(k.minDist, rb);                 // drops the NaN of 0*inf (coincident particles)
-    const f32x2 invr = pack_f32x2(fminf(k.invMinDist, inva), fminf(k.invMinDist, invb));
-    const f32x2 c = sub2(dup2(k.h), pack_f32x2(ra, rb));
-    float ca, cb;
-    unpack_f32x2(c, ca, cb);
-    const bool h0 = (entry & kDuoFlag0) != 0u && ca > 0.f, h1 = (entry & kDuoFlag1) != 0u && cb > 0.f;
-    const f32x2 pterm = mul2(mul2(mul2(c, dup2(k.spiky)), add2(S.pres, dup2(q.w))), invr);
-    float da, db;
-    unpack_f32x2(mul2(S.dens, dup2(u.w)), da, db);
-    float sa, sb;
-    unpack_f32x2(mul2(c, pack_f32x2(fminf(k.minDens, rcp_approx(da)), fminf(k.minDens, rcp_approx(db)))), sa, sb);
-    const f32x2 s = pack_f32x2(h0 ? sa : 0.f, h1 ? sb : 0.f);
-    const f32x2 vt = dup2(k.vterm);
-    S.fx = fma2(fma2(pterm, dx, mul2(vt, sub2(dup2(u.x), S.vx))), s, S.fx);
-    S.fy = fma2(fma2(pterm, dy, mul2(vt, sub2(dup2(u.y), S.vy))), s, S.fy);
-    S.fz = fma2(fma2(pterm, dz, mul2(vt, sub2(dup2(u.z), S.vz))), s, S.fz);
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
 }
 
-// Record decoding: each thread walks the words of its pair, takes the lowest set bit of the union mask as the next
-// neighbour and refills from the (prefetched) next word when the mask runs out.  Only the refill is divergent; the gather
-// and the pair arithmetic run in lock step, two records per iteration so that two gathers are in flight.
-struct DuoCursor {
-    const uint4* col;  uint32_t stride, nw, w, mu;  uint4 cur, nxt;
-    __device__ __forceinline__ void open(const uint4* c, uint32_t s, uint32_t n)
+// Walks the records of one particle: next() returns the sorted index of the next neighbour.  The refill is predicated,
+// not branched (lanes run dry at different iterations, so a branch would be taken by some lane almost every time and
+// split the warp around the pair arithmetic): an empty mask takes the prefetched record and starts the load of the one
+// after it.  Stored records are never empty, so a mask that is still empty after the refill means the stream is done.
+struct RmCursor {
+    const uint2* pn;            // record after `nxt`
+    uint32_t strideBytes, left; // records not yet loaded
+    uint32_t mask, base;  uint2 nxt;
+    __device__ __forceinline__ void open(const uint2* col, uint32_t stride, uint32_t n)
     {
-        col = c;  stride = s;  nw = n;  w = 0u;
-        cur = n > 0u ? __ldg(col) : make_uint4(0u, 0u, 0u, 0u);
-        nxt = n > 1u ? __ldg(col + stride) : make_uint4(0u, 0u, 0u, 0u);
-        mu = cur.y | cur.z;
+        strideBytes = stride * (uint32_t)sizeof(uint2);
+        const uint2 cur = n > 0u ? load_record(col) : make_uint2(0u, 0u);
+        nxt = n > 1u ? load_record(col + stride) : make_uint2(0u, 0u);
+        pn = col + 2 * (size_t)stride;
+        left = n > 2u ? n - 2u : 0u;
+        mask = cur.x;  base = cur.y;
     }
-    // next record: sorted index in the low 30 bits, membership flags of the two particles on top; 0 when exhausted
-    __device__ __forceinline__ uint32_t next()
+    __device__ __forceinline__ bool next(uint32_t& g)
     {
-        if (mu == 0u) {
-            if (w + 1u >= nw) return 0u;
-            w++;
-            cur = nxt;
-            nxt = w + 1u < nw ? __ldg(col + (size_t)(w + 1u) * stride) : make_uint4(0u, 0u, 0u, 0u);
-            mu = cur.y | cur.z;                 // never zero: the density kernel does not store empty words
+        const bool empty = mask == 0u;
+        mask = empty ? nxt.x : mask;
+        base = empty ? nxt.y : base;
+        const bool more = empty && left != 0u;
+        if (empty) nxt = make_uint2(0u, 0u);
+        if (more) {                              // compiles to predicated instructions (one load, three adds)
+            nxt = load_record(pn);
+            pn = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(pn) + strideBytes);
+            left--;
         }
-        const uint32_t b = __ffs(mu) - 1u, bit = 1u << b;
-        mu &= mu - 1u;
-        return (cur.x + b) | ((cur.y & bit) ? kDuoFlag0 : 0u) | ((cur.z & bit) ? kDuoFlag1 : 0u);
+        const bool ok = mask != 0u;
+        const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+        g = ok ? base + b : base;
+        mask &= mask - 1u;
+        return ok;
     }
 };
 
-#ifndef SPH_DUO_FORCE_MIN_BLOCKS
-#define SPH_DUO_FORCE_MIN_BLOCKS 6
-#endif
-__global__ void __launch_bounds__(128, SPH_DUO_FORCE_MIN_BLOCKS)
-k_force_duo(const __grid_constant__ SimParams par, int wordCap,
-            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
-            const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
-            const uint4* __restrict__ records, const uint16_t* __restrict__ nwords,
-            float4* __restrict__ velOut, int first, int n, int ctaFirst)
+__global__ void __launch_bounds__(256)
+k_force_rm(const __grid_constant__ SimParams par, int recCap,
+           const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
+           const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
+           const uint2* __restrict__ records, const uint16_t* __restrict__ nrec,
+           float4* __restrict__ velOut, int first, int n, int ctaFirst, const uint32_t* __restrict__ dev, int part)
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
     const int cta = blockIdx.x + ctaFirst;     // a launch may cover a sub-range of the CTAs the density launch used
-    const int pairIdx = cta * T + threadIdx.x;
-    const int i0 = first + 2 * pairIdx;
-    if (i0 >= n) return;
-    const bool single = i0 + 1 >= n;
-    const int i1 = single ? i0 : i0 + 1;
-    const float4 pp0 = posP[i0], vd0 = velD[i0], pp1 = posP[i1], vd1 = velD[i1];
-    const uint32_t nw = nwords[i0 >> 1];
+    if (dev) {
+        first = (int)__ldg(dev);  n = (int)__ldg(dev + 1);
+        if (!pair_cta_in_part(first + cta * T, T, n, dev, part)) return;
+    }
+    const int i = first + cta * T + threadIdx.x;
+    if (i >= n) return;
+    const float4 pp = posP[i];
+    const float4 vd = velD[i];
+    const float velW = velS[i].w;
+    const uint32_t nw = nrec[i];
 
     ForceConsts k;
     k.h = par.h;  k.minDist = par.minDist;  k.invMinDist = 1.0f / par.minDist;  k.spiky = par.SpikyKern;
     k.vterm = par.LapKern * par.viscosity;  k.minDens = par.minDens;
 
-    float3 f0, f1;
-    if (nw == kDuoInvalid) {                   // record stream overflowed: filtering walk, one particle at a time
-        const bool trunc = __ldg(maxCount) > par.maxParInCell;
-        f0 = force_particle_walk<false>(st, nullptr, 0, posP, velD, cellStart, par, trunc, (uint32_t)i0, keyS[i0], pp0, vd0, k);
-        f1 = single ? make_float3(0.f, 0.f, 0.f)
-                    : force_particle_walk<false>(st, nullptr, 0, posP, velD, cellStart, par, trunc, (uint32_t)i1, keyS[i1], pp1, vd1, k);
-    } else {
-        DuoForceState S;
-        S.px = pack_f32x2(pp0.x, pp1.x);  S.py = pack_f32x2(pp0.y, pp1.y);  S.pz = pack_f32x2(pp0.z, pp1.z);
-        S.vx = pack_f32x2(vd0.x, vd1.x);  S.vy = pack_f32x2(vd0.y, vd1.y);  S.vz = pack_f32x2(vd0.z, vd1.z);
-        S.pres = pack_f32x2(pp0.w, pp1.w);  S.dens = pack_f32x2(vd0.w, vd1.w);
-        S.fx = S.fy = S.fz = dup2(0.f);
-        DuoCursor cur;
-        cur.open(records + (size_t)cta * wordCap * T + threadIdx.x, (uint32_t)T, nw);
+    float3 f = make_float3(0.f, 0.f, 0.f);
+    if (nw != kRmInvalid) {
+        const float3 pi = make_float3(pp.x, pp.y, pp.z), vi = make_float3(vd.x, vd.y, vd.z);
+        RmCursor cur;
+        cur.open(records + (size_t)cta * recCap * T + threadIdx.x, (uint32_t)T, nw);
+        // two neighbours per iteration so that two gathers are in flight
         for (;;) {
-            const uint32_t ea = cur.next();
-            if (ea == 0u) break;
-            uint32_t eb = cur.next();
-            if (eb == 0u) eb = ea & kDuoIndexMask;           // no second record: a valid address with both flags clear
-            const uint32_t ga = ea & kDuoIndexMask, gb = eb & kDuoIndexMask;
+            uint32_t ga, gb;
+            if (!cur.next(ga)) break;
+            const bool two = cur.next(gb);
+            if (!two) gb = ga;
             const float4 qa = __ldg(posP + ga), ua = __ldg(velD + ga);
             const float4 qb = __ldg(posP + gb), ub = __ldg(velD + gb);
-            force_pair_duo(qa, ua, ea, S, k);
-            force_pair_duo(qb, ub, eb, S, k);
+            force_pair(qa, ua, pi, vi, pp.w, vd.w, k, f);
+            if (two) force_pair(qb, ub, pi, vi, pp.w, vd.w, k, f);
         }
-        float ax, bx, ay, by, az, bz;
-        unpack_f32x2(S.fx, ax, bx);  unpack_f32x2(S.fy, ay, by);  unpack_f32x2(S.fz, az, bz);
-        f0 = make_float3(ax, ay, az);  f1 = make_float3(bx, by, bz);
+    } else {
+        const bool trunc = __ldg(maxCount) > par.maxParInCell;
+        f = force_particle_walk<false>(st, nullptr, 0, posP, velD, cellStart, par, trunc, (uint32_t)i, keyS[i], pp, vd, k);
     }
-    velOut[i0] = finish_velocity(par, pp0, vd0, velS[i0].w, f0);
-    if (!single) velOut[i1] = finish_velocity(par, pp1, vd1, velS[i1].w, f1);
+    velOut[i] = finish_velocity(par, pp, vd, velW, f);
 }
+
 
 inline size_t density_smem(const SphPairConfig& c) { return (size_t)c.cap * 16 + (size_t)c.kMax * c.threads * 2; }
 inline size_t force_smem(const SphPairConfig& c) { return (size_t)c.cap * 32 + (size_t)c.kMax * c.threads * 2; }
@@ -1121,12 +1000,12 @@ inline size_t force_smem(const SphPairConfig& c) { return (size_t)c.cap * 32 + (
 
 void sph_pair_default_config(SphPairConfig* cfg)
 {
-    cfg->mode = SPH_PAIR_L1;  cfg->threads = 128;  cfg->cap = 1344;  cfg->kMax = 48;      // kMax must be a multiple of 4
+    cfg->mode = SPH_PAIR_RM;  cfg->threads = 128;  cfg->cap = 24;  cfg->kMax = 48;        // rm: cap = records per particle
 }
 
-const char* sph_pair_mode_name(int mode) { return mode == SPH_PAIR_TMA ? "tma" : mode == SPH_PAIR_DUO ? "duo" : "l1"; }
+const char* sph_pair_mode_name(int mode) { return mode == SPH_PAIR_TMA ? "tma" : mode == SPH_PAIR_RM ? "rm" : "l1"; }
 
-int sph_pair_particles_per_cta(const SphPairConfig& cfg) { return cfg.mode == SPH_PAIR_DUO ? 2 * cfg.threads : cfg.threads; }
+int sph_pair_particles_per_cta(const SphPairConfig& cfg) { return cfg.threads; }
 
 size_t sph_pair_blocks(const SphPairConfig& cfg, int n)
 {
@@ -1134,16 +1013,15 @@ size_t sph_pair_blocks(const SphPairConfig& cfg, int n)
     return ((size_t)n + per - 1) / per;
 }
 
-// duo: `cap` record words of 16 bytes per pair (thread); the others: kMax list entries per particle
+// rm: `cap` records of 8 bytes per particle; the others: kMax list entries per particle
 size_t sph_pair_list_bytes(const SphPairConfig& cfg, int n)
 {
-    if (cfg.mode == SPH_PAIR_DUO) return (sph_pair_blocks(cfg, n) + 1) * (size_t)cfg.cap * cfg.threads * sizeof(uint4);
+    if (cfg.mode == SPH_PAIR_RM) return sph_pair_blocks(cfg, n) * (size_t)cfg.cap * cfg.threads * sizeof(uint2);
     return sph_pair_blocks(cfg, n) * cfg.kMax * cfg.threads * (cfg.mode == SPH_PAIR_TMA ? 2 : 4);
 }
 
 cudaError_t sph_pair_prepare(const SphPairConfig& cfg)
 {
-    if (cfg.mode == SPH_PAIR_DUO) return cudaSuccess;
     if (cfg.mode != SPH_PAIR_TMA) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem(cfg));
     if (e != cudaSuccess) return e;
@@ -1153,25 +1031,27 @@ cudaError_t sph_pair_prepare(const SphPairConfig& cfg)
 void sph_launch_density(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                         const float4* posS, const float4* velS, const uint32_t* keyS, const uint32_t* cellStart,
                         const uint32_t* maxCount, float4* posP, float4* velD, uint32_t* neighborCounts,
-                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count)
+                        void* nlist, uint16_t* ncount, uint32_t* ctaRows, int first, int count, const uint32_t* dev)
 {
     if (count <= 0) return;
     const int n = first + count;
     int blocks = (int)sph_pair_blocks(cfg, count);
-    if (cfg.mode == SPH_PAIR_DUO) {
-        // SPH_B200_DUO_OCC=8|9|10 (tuning aid): occupancy target of the density kernel
-        static const int occ = [] { const char* e = getenv("SPH_B200_DUO_OCC");  const int v = e ? atoi(e) : 9;  return v >= 8 && v <= 10 ? v : 9; }();
+    if (cfg.mode == SPH_PAIR_RM) {
+        // SPH_B200_RM_OCC=12|16 (tuning aid): resident 128-thread CTAs per SM the density kernel is compiled for
+        static const int occ = [] { const char* e = getenv("SPH_B200_RM_OCC");  return e && atoi(e) == 16 ? 16 : 12; }();
+        static const int unr = [] { const char* e = getenv("SPH_B200_RM_UNROLL");  return e && atoi(e) == 2 ? 2 : 4; }();
         auto launch = [&](auto kern) {
-            kern<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount, posP, velD,
-                                                       neighborCounts, (uint4*)nlist, ncount, first, n);
+            kern<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posS, velS, keyS, cellStart, maxCount,
+                                                       posP, velD, neighborCounts, (uint2*)nlist, ncount, first, n, dev);
         };
-        if (occ == 10) launch(k_density_duo<10>);  else if (occ == 8) launch(k_density_duo<8>);  else launch(k_density_duo<9>);
+        if (occ == 16) { if (unr == 2) launch(k_density_rm<16, 2>);  else launch(k_density_rm<16, 4>); }
+        else           { if (unr == 2) launch(k_density_rm<12, 2>);  else launch(k_density_rm<12, 4>); }
     } else if (cfg.mode == SPH_PAIR_TMA)
         k_density<<<blocks, cfg.threads, density_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
                                                                         posP, velD, neighborCounts, (uint16_t*)nlist, ncount, ctaRows, first, n);
     else
         k_density_l1<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posS, velS, keyS, cellStart, maxCount,
-                                                           posP, velD, neighborCounts, (uint32_t*)nlist, ncount, first, n);
+                                                           posP, velD, neighborCounts, (uint32_t*)nlist, ncount, first, n, dev);
     SPH_COUNT(L);
 }
 
@@ -1185,7 +1065,8 @@ static bool force_list_streaming()
 void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimParams& par,
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
-                      const uint32_t* ctaRows, float4* velOut, int first, int count, int ctaFirst, int ctaCount)
+                      const uint32_t* ctaRows, float4* velOut, int first, int count, int ctaFirst, int ctaCount,
+                      const uint32_t* dev, int part)
 {
     if (count <= 0) return;
     const int n = first + count;
@@ -1195,17 +1076,17 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
         if (ctaCount <= 0) return;
         blocks = ctaCount;
     } else ctaFirst = 0;
-    if (cfg.mode == SPH_PAIR_DUO)
-        k_force_duo<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
-                                                                            (const uint4*)nlist, ncount, velOut, first, n, ctaFirst);
+    if (cfg.mode == SPH_PAIR_RM)
+        k_force_rm<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
+                                                         (const uint2*)nlist, ncount, velOut, first, n, ctaFirst, dev, part);
     else if (cfg.mode == SPH_PAIR_TMA)
         k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
                                                                     (const uint16_t*)nlist, ncount, ctaRows, velOut, first, n);
     else if (force_list_streaming())
         k_force_l1<true><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                               (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst);
+                                                               (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst, dev, part);
     else
         k_force_l1<false><<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
-                                                                (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst);
+                                                                (const uint32_t*)nlist, ncount, velOut, first, n, ctaFirst, dev, part);
     SPH_COUNT(L);
 }

@@ -686,6 +686,217 @@ __global__ void k_slab_scan_bound(uint32_t* __restrict__ keyMaxSlots, uint32_t g
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Slab mode with device-resident bookkeeping (the multi-GPU driver, sph_capi.cu "multi-GPU driver").  The ranges the
+// host used to read back after every sort live in the state words st[] (SlabDevWord, sph_device.cuh); kernels are
+// launched over upper bounds and find their own ranges, so a step never synchronises with the host.
+
+// Phase A: integrate the first and the last owned layer only and pack what the neighbours need from them (leavers, copies
+// of the boundary layers).  Thread t < nLo handles slot first + t, the next nHi threads the slots from bHi on.
+__global__ void __launch_bounds__(256)
+k_slab_boundary_integrate_pack(const __grid_constant__ SimParams par, const BoundaryCtx ctx, float4* __restrict__ pos,
+                               float4* __restrict__ vel, uint32_t* __restrict__ idx, uint32_t* __restrict__ st,
+                               int zLo, int zHi, int hasLower, int hasUpper,
+                               SlabRecord* __restrict__ leavDown, SlabRecord* __restrict__ leavUp, int capL,
+                               SlabRecord* __restrict__ bndDown, SlabRecord* __restrict__ bndUp, int capB,
+                               uint32_t* __restrict__ headDown, uint32_t* __restrict__ headUp)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO], bHi = st[SD_BHI];
+    const uint32_t nLo = bLo - g0, nHi = g1 - bHi;
+    // the launch covers 2 * capB slots; a fuller layer does not fit the message either
+    if (t == 0 && nLo + nHi > gridDim.x * blockDim.x) st[SD_OVERFLOW] = 1u;
+    const bool active = t < nLo + nHi;
+    const uint32_t i = t < nLo ? g0 + t : bHi + (t - nLo);
+    uint32_t id = kDeadIndex;
+    float4 pOut = make_float4(0.f, 0.f, 0.f, 0.f), vOut = pOut;
+    bool goDown = false, goUp = false, copyDown = false, copyUp = false;
+    if (active) {
+        id = idx[i];
+        const float4 p4 = pos[i], v4 = vel[i];
+        float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
+        integrate_particle(par, ctx, p, v);
+        pOut = make_float4(p.x, p.y, p.z, p4.w);
+        vOut = make_float4(v.x, v.y, v.z, v4.w);
+        pos[i] = pOut;
+        vel[i] = vOut;
+        if (id != kDeadIndex) {
+            const int zc = z_cell(par, p.z);
+            goDown = zc < zLo && hasLower;
+            goUp = zc >= zHi && hasUpper;
+            copyDown = zc == zLo && hasLower;
+            copyUp = zc == zHi - 1 && hasUpper && zc >= zLo;
+        }
+    }
+    const uint32_t sLeavDown = warp_append_slot(headDown + 0, goDown), sLeavUp = warp_append_slot(headUp + 0, goUp);
+    const uint32_t sBndDown = warp_append_slot(headDown + 1, copyDown), sBndUp = warp_append_slot(headUp + 1, copyUp);
+    if (!(goDown || goUp || copyDown || copyUp)) return;
+    SlabRecord r;  r.pos = pOut;  r.vel = vOut;  r.meta = make_uint4(id, 0u, 0u, 0u);
+    if (goDown) { if (sLeavDown < (uint32_t)capL) leavDown[sLeavDown] = r; }
+    else if (goUp) { if (sLeavUp < (uint32_t)capL) leavUp[sLeavUp] = r; }
+    if (goDown || goUp) idx[i] = kDeadIndex;
+    if (copyDown && sBndDown < (uint32_t)capB) bndDown[sBndDown] = r;
+    if (copyUp && sBndUp < (uint32_t)capB) bndUp[sBndUp] = r;
+}
+
+// local key of a live particle: global hash minus the slab's offset; anything outside the local table goes to the dummy
+// cell numCellsLocal, which sorts behind every real cell.  An OWNED particle outside the owned key range was moved by more
+// than one cell layer in a step (or teleported): the decomposition cannot follow it, which is reported, not hidden.
+__device__ __forceinline__ uint32_t slab_local_key(const SimParams& par, float4 p, long long keyOffset, int numCellsLocal,
+                                                   bool mustBeOwned, uint32_t ownedLo, uint32_t ownedHi, uint32_t* __restrict__ st)
+{
+    const long long k = (long long)cell_hash(par, make_float3(p.x, p.y, p.z)) - keyOffset;
+    const bool inTable = k >= 0 && k < (long long)numCellsLocal;
+    if (mustBeOwned && !(inTable && (uint32_t)k >= ownedLo && (uint32_t)k < ownedHi)) atomicOr(&st[SD_LOST], 1u);
+    return inTable ? (uint32_t)k : (uint32_t)numCellsLocal;
+}
+
+// Phase B, over the whole work set while exchange 1 is in flight: integrate the owned particles between the two boundary
+// layers (split != 0), retire every slot that is not owned (last step's ghosts and dead slots), and hash + count all slots.
+__global__ void __launch_bounds__(256)
+k_slab_interior_hist(const __grid_constant__ SimParams par, const BoundaryCtx ctx, float4* __restrict__ pos, float4* __restrict__ vel,
+                     uint32_t* __restrict__ idx, uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU,
+                     uint32_t* __restrict__ cellCount, uint32_t* __restrict__ st, long long keyOffset, int numCellsLocal,
+                     uint32_t ownedLo, uint32_t ownedHi, uint32_t* __restrict__ keyMaxSlots, int split)
+{
+    __shared__ uint32_t blockMax;
+    if (threadIdx.x == 0) blockMax = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t work = st[SD_WORK];
+    if (i == 0) st[SD_WORK0] = work;            // the unpack kernel appends behind this
+    uint32_t live1 = 0;
+    if (i < work) {
+        const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO], bHi = st[SD_BHI];
+        const bool owned = i >= g0 && i < g1;
+        uint32_t id = idx[i];
+        if (!owned && id != kDeadIndex) { idx[i] = kDeadIndex;  id = kDeadIndex; }
+        uint32_t key = (uint32_t)numCellsLocal;
+        if (id != kDeadIndex) {
+            float4 p4 = pos[i];
+            if (split && i >= bLo && i < bHi) {
+                const float4 v4 = vel[i];
+                float3 p = make_float3(p4.x, p4.y, p4.z), v = make_float3(v4.x, v4.y, v4.z);
+                integrate_particle(par, ctx, p, v);
+                p4 = make_float4(p.x, p.y, p.z, p4.w);
+                pos[i] = p4;
+                vel[i] = make_float4(v.x, v.y, v.z, v4.w);
+            }
+            key = slab_local_key(par, p4, keyOffset, numCellsLocal, true, ownedLo, ownedHi, st);
+            if (key != (uint32_t)numCellsLocal) live1 = key + 1;
+        }
+        keyU[i] = key;
+        rankU[i] = atomicAdd(&cellCount[key], 1u);
+    }
+    live1 = __reduce_max_sync(0xffffffffu, live1);
+    if ((threadIdx.x & 31) == 0 && live1) atomicMax(&blockMax, live1);
+    __syncthreads();
+    if (threadIdx.x == 0 && blockMax) atomicMax(&keyMaxSlots[blockIdx.x & (kKeyMaxSlots - 1)], blockMax);
+}
+
+// k_slab_unpack with the work-set size on the device and the hash + count of every appended record fused in
+__global__ void __launch_bounds__(256)
+k_slab_unpack_hist(const __grid_constant__ SimParams par, const SlabRecord* __restrict__ inBelow, const SlabRecord* __restrict__ inAbove,
+                   const SlabRecord* __restrict__ ownDown, const SlabRecord* __restrict__ ownUp, int capL, int capB,
+                   float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ idx, int capacity,
+                   uint32_t* __restrict__ keyU, uint32_t* __restrict__ rankU, uint32_t* __restrict__ cellCount,
+                   uint32_t* __restrict__ st, long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi,
+                   uint32_t* __restrict__ keyMaxSlots)
+{
+    const SlabRecord* msg[6] = {inBelow, inAbove, inBelow, inAbove, ownDown, ownUp};
+    const int word[6] = {0, 0, 1, 1, 0, 0};
+    const int row0[6] = {1, 1, 1 + capL, 1 + capL, 1, 1};
+    const int cap[6]  = {capL, capL, capB, capB, capL, capL};
+    const int sec = blockIdx.y;
+    const uint32_t work0 = st[SD_WORK0];
+    uint32_t cnt[6], off = 0, total = 0, over = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t c = msg[k] ? reinterpret_cast<const uint32_t*>(msg[k])[word[k]] : 0u;
+        if (c > (uint32_t)cap[k]) { over = 1;  c = (uint32_t)cap[k]; }
+        cnt[k] = c;
+        if (k < sec) off += c;
+        total += c;
+    }
+    if ((long long)work0 + total > capacity) over = 1;
+    if (sec == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        st[SD_WORK] = (uint32_t)min((long long)work0 + total, (long long)capacity);
+        if (over) st[SD_OVERFLOW] = 1u;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mine = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; k++) if (k == sec) mine = cnt[k];
+    uint32_t live1 = 0;
+    const long long dst = (long long)work0 + off + i;
+    if (i < (int)mine && dst < capacity) {
+        const SlabRecord* src = nullptr;  int r0 = 0;
+        #pragma unroll
+        for (int k = 0; k < 6; k++) if (k == sec) { src = msg[k];  r0 = row0[k]; }
+        const SlabRecord r = src[r0 + i];
+        pos[dst] = r.pos;  vel[dst] = r.vel;  idx[dst] = r.meta.x;
+        // sections 0 and 1 are arrivals: they are owned here from now on
+        const uint32_t key = slab_local_key(par, r.pos, keyOffset, numCellsLocal, sec < 2, ownedLo, ownedHi, st);
+        if (key != (uint32_t)numCellsLocal) live1 = key + 1;
+        keyU[dst] = key;
+        rankU[dst] = atomicAdd(&cellCount[key], 1u);
+    }
+    live1 = __reduce_max_sync(0xffffffffu, live1);
+    if ((threadIdx.x & 31) == 0 && live1) atomicMax(&keyMaxSlots[(blockIdx.x + 7 * blockIdx.y) & (kKeyMaxSlots - 1)], live1);
+}
+
+// After the scan: the sorted ranges (ghosts below | owned | ghosts above) and the two boundary layers, from five cell-table
+// entries.  Entries at or above the scan bound were not written this step: no live key is that large, so they equal the
+// live total, which is the start of the dummy cell (always scanned).
+__global__ void k_slab_bounds(const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ scanBound, uint32_t* __restrict__ st,
+                              int c0, int c1, int c2, int c3, int c4, int hasLower, int hasUpper)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int cells[5] = {c0, c1, c2, c3, c4};
+    const int bound = (int)*scanBound, lastTileStart = c2 / SPH_SCAN_TILE * SPH_SCAN_TILE;
+    uint32_t v[5];
+    const uint32_t total = cellStart[c2];
+    for (int k = 0; k < 5; k++) v[k] = (cells[k] >= bound && cells[k] < lastTileStart) ? total : cellStart[cells[k]];
+    st[SD_FIRST] = v[0];  st[SD_END] = v[1];  st[SD_G2] = v[2];
+    st[SD_BLO] = hasLower ? v[3] : v[0];        // no neighbour on a side: no boundary layer there
+    st[SD_BHI] = hasUpper ? v[4] : v[1];
+}
+
+// rho,p rows of the two boundary layers: [0] = {count, 0, 0, 0}, then (x,y,z,p), (vx,vy,vz,rho) per particle
+__global__ void __launch_bounds__(256)
+k_slab_pack_dp(const float4* __restrict__ posP, const float4* __restrict__ velD, uint32_t* __restrict__ st,
+               float4* __restrict__ dpDown, float4* __restrict__ dpUp, int capRows)
+{
+    const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO], bHi = st[SD_BHI];
+    const uint32_t nDown = bLo - g0, nUp = g1 - bHi;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        dpDown[0] = make_float4(__uint_as_float(min(nDown, (uint32_t)capRows)), 0.f, 0.f, 0.f);
+        dpUp[0] = make_float4(__uint_as_float(min(nUp, (uint32_t)capRows)), 0.f, 0.f, 0.f);
+        if (nDown > (uint32_t)capRows || nUp > (uint32_t)capRows) st[SD_OVERFLOW] = 1u;
+    }
+    if (blockIdx.y == 0) { if (t < nDown && t < (uint32_t)capRows) { dpDown[1 + 2 * t] = posP[g0 + t];  dpDown[2 + 2 * t] = velD[g0 + t]; } }
+    else                 { if (t < nUp && t < (uint32_t)capRows)   { dpUp[1 + 2 * t] = posP[bHi + t];   dpUp[2 + 2 * t] = velD[bHi + t]; } }
+}
+
+// the neighbours' rows become the (x,y,z,p) / (v,rho) of this rank's ghosts, which sort in the same order on both sides
+__global__ void __launch_bounds__(256)
+k_slab_unpack_dp(const float4* __restrict__ dpBelow, const float4* __restrict__ dpAbove, uint32_t* __restrict__ st,
+                 float4* __restrict__ posP, float4* __restrict__ velD)
+{
+    const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], g2 = st[SD_G2];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.y == 0) {
+        const uint32_t n = dpBelow ? __float_as_uint(dpBelow[0].x) : 0u;
+        if (t == 0 && n != g0) st[SD_DPERR] = 1u;               // ghost sets out of step between the ranks
+        if (t < n && t < g0) { posP[t] = dpBelow[1 + 2 * t];  velD[t] = dpBelow[2 + 2 * t]; }
+    } else {
+        const uint32_t n = dpAbove ? __float_as_uint(dpAbove[0].x) : 0u;
+        if (t == 0 && n != g2 - g1) st[SD_DPERR] = 1u;
+        if (t < n && t < g2 - g1) { posP[g1 + t] = dpAbove[1 + 2 * t];  velD[g1 + t] = dpAbove[2 + 2 * t]; }
+    }
+}
+
 inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
 }  // namespace
@@ -830,5 +1041,70 @@ void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void*
     dim3 grid(blocks_for(m, 256), 6);
     k_slab_unpack<<<grid, 256, 0, L.stream>>>((const SlabRecord*)inBelow, (const SlabRecord*)inAbove, (const SlabRecord*)ownDown,
                                               (const SlabRecord*)ownUp, capL, capB, pos, vel, idx, work0, capacity, dev);
+    SPH_COUNT(L);
+}
+
+// ---- slab mode, device-resident bookkeeping -------------------------------------------------------
+void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                             uint32_t* st, int zLo, int zHi, int hasLower, int hasUpper,
+                                             void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
+                                             uint32_t* headDown, uint32_t* headUp)
+{
+    const BoundaryCtx ctx = boundary_ctx(par);
+    // a boundary layer holds at most capB particles (more would overflow the message anyway)
+    k_slab_boundary_integrate_pack<<<blocks_for(2 * capB, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, st, zLo, zHi, hasLower, hasUpper,
+                                                                                  (SlabRecord*)leavDown, (SlabRecord*)leavUp, capL,
+                                                                                  (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_interior_hist(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
+                                   uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, uint32_t* st, int bound,
+                                   long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi,
+                                   uint32_t* keyMaxSlots, int split)
+{
+    const BoundaryCtx ctx = boundary_ctx(par);
+    k_slab_interior_hist<<<blocks_for(bound, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, keyU, rankU, cellCount, st, keyOffset,
+                                                                      numCellsLocal, ownedLo, ownedHi, keyMaxSlots, split);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_unpack_hist(const SphLaunch& L, const SimParams& par, const void* inBelow, const void* inAbove,
+                                 const void* ownDown, const void* ownUp, int capL, int capB, float4* pos, float4* vel, uint32_t* idx,
+                                 int capacity, uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, uint32_t* st,
+                                 long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi, uint32_t* keyMaxSlots)
+{
+    const int m = capL > capB ? capL : capB;
+    dim3 grid(blocks_for(m, 256), 6);
+    k_slab_unpack_hist<<<grid, 256, 0, L.stream>>>(par, (const SlabRecord*)inBelow, (const SlabRecord*)inAbove, (const SlabRecord*)ownDown,
+                                                   (const SlabRecord*)ownUp, capL, capB, pos, vel, idx, capacity, keyU, rankU, cellCount,
+                                                   st, keyOffset, numCellsLocal, ownedLo, ownedHi, keyMaxSlots);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_scan_bound(const SphLaunch& L, uint32_t* keyMaxSlots, uint32_t guardCells, int numCellsLocal)
+{
+    k_slab_scan_bound<<<1, 32, 0, L.stream>>>(keyMaxSlots, guardCells, (uint32_t)numCellsLocal);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_bounds(const SphLaunch& L, const uint32_t* cellStart, const uint32_t* scanBound, uint32_t* st,
+                            const int cells[5], int hasLower, int hasUpper)
+{
+    k_slab_bounds<<<1, 32, 0, L.stream>>>(cellStart, scanBound, st, cells[0], cells[1], cells[2], cells[3], cells[4], hasLower, hasUpper);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_pack_dp(const SphLaunch& L, const float4* posP, const float4* velD, uint32_t* st, float4* dpDown, float4* dpUp, int capRows)
+{
+    dim3 grid(blocks_for(capRows, 256), 2);
+    k_slab_pack_dp<<<grid, 256, 0, L.stream>>>(posP, velD, st, dpDown, dpUp, capRows);
+    SPH_COUNT(L);
+}
+
+void sph_launch_slab_unpack_dp(const SphLaunch& L, const float4* dpBelow, const float4* dpAbove, uint32_t* st, float4* posP, float4* velD, int capRows)
+{
+    dim3 grid(blocks_for(capRows, 256), 2);
+    k_slab_unpack_dp<<<grid, 256, 0, L.stream>>>(dpBelow, dpAbove, st, posP, velD);
     SPH_COUNT(L);
 }

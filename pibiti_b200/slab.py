@@ -538,7 +538,7 @@ def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
     dom = max((k for k in ("density", "force") if k in kernel_ms), key=lambda k: kernel_ms[k], default=None)
     if dom is not None and kernel_ms[dom] > 0:
         achieved = stage_bytes[dom] * owned_timed / (kernel_ms[dom] * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": {"density": "k_density_l1", "force": "k_force_l1"}[dom],
+        out["roofline"] = {"bound": "hbm", "kernel": {"density": "k_density_rm", "force": "k_force_rm"}[dom],
                            "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                            "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_particle": stage_bytes[dom],
                            "note": "rank 0, last timed step, owned particles only; the single-GPU line carries the ncu traffic",

@@ -69,7 +69,25 @@ def test_density_kernel_is_packed_predicated_and_register_lean(sass, resources):
     assert res["reg"] <= 32 and res["stack"] == 0 and res["local"] == 0
 
 
+def test_row_mask_density_kernel_is_exact_predicated_and_store_free_in_the_walk(sass, resources):
+    """The default (rm) density kernel: packed but uncontracted distance, predicated sum / mask updates, and no store per
+    candidate -- the only stores are the per-record ones and the four per-particle results."""
+    codes = _one(sass, "12k_density_rmILi12ELi4")
+    (code,) = codes
+    text = "\n".join(code)
+    assert "FADD2" in text and "FMUL2" in text and "FFMA2" not in text
+    assert re.search(r"@!?P\d FFMA ", text) and re.search(r"@!?P\d LOP3\.LUT ", text)
+    assert not any(i.startswith(("STL", "LDL")) for i in code)
+    loads = sum(1 for i in code if "LDG.E.128" in i)
+    stores = sum(1 for i in code if re.search(r"\bSTG\.", i))
+    assert stores <= 12 and loads > 3 * stores, (loads, stores)
+    (res,) = _one(resources, "12k_density_rmILi12ELi4")
+    assert res["reg"] <= 40 and res["stack"] == 0 and res["local"] == 0
+
+
 def test_force_kernel_register_budget(resources):
+    for res in _one(resources, "10k_force_rm"):
+        assert res["reg"] <= 64
     for res in _one(resources, "10k_force_l1"):
         assert res["reg"] <= 64 and res["stack"] == 0
 
