@@ -172,6 +172,41 @@ int sph_slab_force_part(sph_t* s, int part);
 /* diagnostics after a step: {largest real cell, work-set size, ghosts below, owned, ghosts above, retired slots} */
 int sph_slab_stats(sph_t* s, int* out6);
 
+/* ---- multi-GPU driver: the whole system on several GPUs of one box, z-slab decomposed -----------------------------
+ * New in this library (the reference is single-GPU: one cSPH, source/SPH/SPH.h:9-50, one device).  A sph_multi_t owns
+ * one slab handle per GPU it drives and steps them from one host thread with no host synchronisation inside a step;
+ * neighbouring slabs exchange particle messages and (density, pressure) rows with ncclSend / ncclRecv over NVLink on a
+ * second stream per slab (no collective on the data path).  Results are bit-identical to the single-GPU step.
+ * Two shapes:  sph_multi_create       one process drives `ndev` GPUs (what a C++ App holding a cSPH uses);
+ *              sph_multi_create_rank  one process per GPU, `world` processes (bench.py under torchrun); the NCCL unique id
+ *                                     comes from sph_multi_unique_id on one process and is handed to the others by the
+ *                                     launcher.
+ * capacityPerSlab = particle slots of a slab: its owned particles plus ghosts and arrivals of a step.
+ * Not supported (rejected): the Z wrap/cycle teleport and the pump boundary, which move particles across slabs. */
+typedef struct sph_multi sph_multi_t;
+int sph_multi_unique_id(unsigned char* id128);                                   /* 128 bytes (ncclUniqueId) */
+int sph_multi_create(const struct SimParams* params, int ndev, const int* devices, int capacityPerSlab, sph_multi_t** out);
+int sph_multi_create_rank(const struct SimParams* params, int rank, int world, const unsigned char* id128, int device,
+                          int capacityPerSlab, sph_multi_t** out);
+int sph_multi_destroy(sph_multi_t* m);
+const char* sph_multi_last_error(sph_multi_t* m);
+int sph_multi_set_params(sph_multi_t* m, const struct SimParams* params);       /* setParameters, every slab */
+/* The whole system from HOST float4 arrays in ORIGINAL particle order (cSPH::setArray for both arrays at once; every
+ * process passes the same arrays).  cuts: world+1 z-layer boundaries, or NULL to balance the particle counts. */
+int sph_multi_set_state(sph_multi_t* m, const float* pos, const float* vel, int n, const int* cuts);
+/* cSPH::Update: nsteps solver steps, asynchronous.  Device-side problems (message overflow, a particle that moved more
+ * than one cell layer in a step) surface at the next sph_multi_sync / sph_multi_get_state. */
+int sph_multi_step(sph_multi_t* m, int nsteps);
+int sph_multi_sync(sph_multi_t* m);
+/* cSPH::getArray: owned particles of this process's slabs into HOST arrays indexed by original particle id (float4 rows
+ * for pos / vel, one float for dens / pres; NULL to skip).  Rows owned by other processes are left untouched. */
+int sph_multi_get_state(sph_multi_t* m, float* pos, float* vel, float* dens, float* pres, int n, int* written);
+int sph_multi_local_slabs(sph_multi_t* m);
+sph_t* sph_multi_handle(sph_multi_t* m, int local);                             /* timings, dumps, launch counts of one slab */
+void* sph_multi_stream(sph_multi_t* m, int local);                              /* cudaStream_t the slab's kernels run on */
+/* z cuts [world+1], owned particles of the LOCAL slabs, {leaver, boundary} record capacities, bytes sent so far */
+int sph_multi_info(sph_multi_t* m, int* cuts, int* ownedLocal, int* capLB2, unsigned long long* bytesSent);
+
 #ifdef __cplusplus
 }
 #endif

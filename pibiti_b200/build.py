@@ -31,6 +31,7 @@ CUDA_UNITS = {
     "sph_pair_kernels.cu": [],
     "sph_extras_kernels.cu": [],
     "sph_capi.cu": [],
+    "sph_multi.cu": [],           # multi-GPU driver; NCCL is dlopen'ed at run time
 }
 HOST_UNITS = sorted(p.name for p in (CSRC / "host").glob("*.cpp")) if (CSRC / "host").is_dir() else []
 

@@ -89,10 +89,13 @@ enum SlabDevWord {
     SD_BHI = 11,
     SD_G2 = 12,         // ghosts above = [SD_END, SD_G2); ghosts below = [0, SD_FIRST)
     SD_DPERR = 13,      // rho,p rows received != ghosts expected
+    SD_BLO2 = 14,       // the first TWO owned layers = [SD_FIRST, SD_BLO2), the last two = [SD_BHI2, SD_END): every particle
+    SD_BHI2 = 15,       // that can leave the slab or land in a boundary layer within one step (it moves at most one layer)
     SD_WORDS = 16
 };
 void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
-                                             uint32_t* st, int zLo, int zHi, int hasLower, int hasUpper,
+                                             uint32_t* st, int bound /* threads: >= particles of the two-layer edge regions */,
+                                             int zLo, int zHi, int hasLower, int hasUpper,
                                              void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
                                              uint32_t* headDown, uint32_t* headUp);
 void sph_launch_slab_interior_hist(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
@@ -105,7 +108,7 @@ void sph_launch_slab_unpack_hist(const SphLaunch& L, const SimParams& par, const
                                  long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi, uint32_t* keyMaxSlots);
 void sph_launch_slab_scan_bound(const SphLaunch& L, uint32_t* keyMaxSlots, uint32_t guardCells, int numCellsLocal);
 void sph_launch_slab_bounds(const SphLaunch& L, const uint32_t* cellStart, const uint32_t* scanBound, uint32_t* st,
-                            const int cells[5], int hasLower, int hasUpper);
+                            const int cells[7], int hasLower, int hasUpper);
 void sph_launch_slab_pack_dp(const SphLaunch& L, const float4* posP, const float4* velD, uint32_t* st, float4* dpDown, float4* dpUp, int capRows);
 void sph_launch_slab_unpack_dp(const SphLaunch& L, const float4* dpBelow, const float4* dpAbove, uint32_t* st, float4* posP, float4* velD, int capRows);
 

@@ -1,0 +1,628 @@
+// sph_multi.cu -- the multi-GPU driver behind sph_multi_* (include/sph_b200.h): one SPH system cut into z slabs, one slab
+// per GPU, stepped from ONE host thread with no host synchronisation inside a step.
+//
+// The reference is single-GPU (one cSPH, source/SPH/SPH.h:9-50); this is the layer that lets a cSPH hold more than one
+// device.  Two shapes share the code:
+//   * one process drives ndev GPUs            (sph_multi_create:      ncclCommInitAll, a C++ App holding a cSPH)
+//   * one process per GPU, `world` processes  (sph_multi_create_rank: ncclCommInitRank from a shared unique id; how
+//                                              bench.py runs under torchrun)
+// Every slab is an sph_t handle in slab mode whose bookkeeping (work-set size, sorted ranges, boundary layers) lives in
+// device words (SlabDevWord, sph_device.cuh); kernels are launched over upper bounds and find their own ranges.
+//
+// One step, per slab (S = the handle's stream, X = the slab's exchange stream):
+//   S  A  integrate the first two / last two owned layers, pack leavers + boundary-layer copies      k_slab_boundary_integrate_pack
+//   X     exchange 1: particle messages to / from the z neighbours (ncclSend / ncclRecv, grouped)    -- overlaps B
+//   S  B  integrate the layers in between, retire last step's ghosts, hash + count every slot        k_slab_interior_hist
+//   S     append arrivals and ghosts, hash + count them                                              k_slab_unpack_hist
+//   S     bounded scan, bucket, stable rank + gather (same in-cell order as the single-GPU sort), ranges to device words
+//   S     density of the owned particles, rho,p rows of the two boundary layers                      k_density_*, k_slab_pack_dp
+//   X     exchange 2: rho,p rows                                                                     -- overlaps the interior force
+//   S     force of the CTAs without ghost neighbours; then the received rows, then the remaining CTAs
+// Exchanges are nearest-neighbour only; there is no collective on the data path.  NCCL is loaded at run time
+// (libnccl.so.2), so the single-GPU entry points do not depend on it.
+#include "sph_internal.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+
+NcclApi g_nccl;
+
+// dlopen by soname first: in a process that already carries an NCCL (PyTorch's bundled copy) this returns that one
+bool load_nccl(std::string& why)
+{
+    if (g_nccl.lib) return true;
+    const char* names[] = {getenv("SPH_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { why = std::string("libnccl.so.2 not found (set SPH_B200_NCCL_LIB): ") + (dlerror() ? dlerror() : "");  return false; }
+    NcclApi a;
+    a.lib = h;
+#define SYM(field, name)                                                              \
+    *(void**)(&a.field) = dlsym(h, name);                                             \
+    if (!a.field) { why = std::string("NCCL symbol missing: ") + name;  return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")  SYM(CommInitRank, "ncclCommInitRank")  SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")  SYM(GroupStart, "ncclGroupStart")      SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")                SYM(Recv, "ncclRecv")                  SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GetVersion, "ncclGetVersion")
+#undef SYM
+    g_nccl = a;
+    return true;
+}
+
+constexpr int kRecFloats = SPH_SLAB_RECORD_FLOATS;     // 12 floats = 48 bytes per particle record
+
+struct MultiRank {
+    sph_system* s = nullptr;
+    int device = 0, rank = 0;                   // CUDA device, global slab index
+    int zLo = 0, zHi = 0, hasLower = 0, hasUpper = 0;
+    int capacity = 0;
+    cudaStream_t xs = nullptr;                  // exchange stream
+    ncclComm_t comm = nullptr;
+    float *msgDown = nullptr, *msgUp = nullptr, *inBelow = nullptr, *inAbove = nullptr;      // particle messages
+    float4 *dpDown = nullptr, *dpUp = nullptr, *dpBelow = nullptr, *dpAbove = nullptr;       // rho,p rows
+    cudaEvent_t evA = nullptr, evX1 = nullptr, evDp = nullptr, evX2 = nullptr;
+    uint32_t* hostSt = nullptr;                 // pinned copy of the device words
+    int owned = 0;                              // as of the last sph_multi_sync / set_state
+};
+
+}  // namespace
+
+struct sph_multi {
+    std::vector<MultiRank> ranks;               // the slabs this process drives
+    int world = 1;
+    std::vector<int> cuts;                      // world + 1 z-layer boundaries
+    SimParams par;                              // global parameters (numParticles = particles of the whole system)
+    int capL = 0, capB = 0;                     // message sections: leavers, boundary-layer copies (records)
+    bool haveState = false;
+    bool copyExchange = false;                  // one process: neighbours' buffers are copied directly (cudaMemcpyPeerAsync)
+                                                // instead of ncclSend/ncclRecv -- also what lets several slabs share one GPU
+    long long steps = 0;
+    unsigned long long bytesSent = 0;
+    std::string err;
+};
+
+namespace {
+
+std::string g_multiCreateError;
+
+int mfail(sph_multi* m, int code, const char* fmt, ...)
+{
+    char buf[640];
+    va_list ap;  va_start(ap, fmt);  vsnprintf(buf, sizeof buf, fmt, ap);  va_end(ap);
+    if (m) m->err = buf; else g_multiCreateError = buf;
+    return code;
+}
+
+#define MCU(m, call)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return mfail((m), SPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define MNCCL(m, call)                                                                                 \
+    do {                                                                                               \
+        ncclResult_t _r = (call);                                                                      \
+        if (_r != ncclSuccess)                                                                         \
+            return mfail((m), SPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+size_t msg_rows(const sph_multi* m) { return 1 + (size_t)m->capL + m->capB; }
+size_t msg_bytes(const sph_multi* m) { return msg_rows(m) * kRecFloats * sizeof(float); }
+size_t dp_bytes(const sph_multi* m) { return (1 + 2 * (size_t)m->capB) * sizeof(float4); }
+
+// z cell layer of a particle, the same float arithmetic as z_cell() in sph_stream_kernels.cu
+inline int host_z_cell(const SimParams& p, float z) { return (int)floorf((z - p.worldMin.z) / p.cellSize.z); }
+
+void free_messages(MultiRank& r)
+{
+    cudaSetDevice(r.device);
+    void* bufs[] = {r.msgDown, r.msgUp, r.inBelow, r.inAbove, r.dpDown, r.dpUp, r.dpBelow, r.dpAbove};
+    for (void* b : bufs) if (b) cudaFree(b);
+    r.msgDown = r.msgUp = r.inBelow = r.inAbove = nullptr;
+    r.dpDown = r.dpUp = r.dpBelow = r.dpAbove = nullptr;
+}
+
+int alloc_messages(sph_multi* m, MultiRank& r)
+{
+    free_messages(r);
+    MCU(m, cudaSetDevice(r.device));
+    float** pm[] = {&r.msgDown, &r.msgUp, &r.inBelow, &r.inAbove};
+    for (float** p : pm) { MCU(m, cudaMalloc((void**)p, msg_bytes(m)));  MCU(m, cudaMemset(*p, 0, msg_bytes(m))); }
+    float4** pd[] = {&r.dpDown, &r.dpUp, &r.dpBelow, &r.dpAbove};
+    for (float4** p : pd) { MCU(m, cudaMalloc((void**)p, dp_bytes(m)));  MCU(m, cudaMemset(*p, 0, dp_bytes(m))); }
+    return SPH_OK;
+}
+
+// layer boundaries giving every slab about the same particle count (at least minLayers layers each)
+bool cut_layers(const std::vector<long long>& hist, int ranks, int minLayers, std::vector<int>& cuts)
+{
+    const int gz = (int)hist.size();
+    std::vector<long long> cum(gz);
+    long long run = 0;
+    for (int k = 0; k < gz; k++) { run += hist[k];  cum[k] = run; }
+    cuts.assign(1, 0);
+    for (int r = 1; r < ranks; r++) {
+        const double target = (double)run * r / ranks;
+        int c = (int)(std::lower_bound(cum.begin(), cum.end(), (long long)std::ceil(target)) - cum.begin()) + 1;
+        c = std::max(c, cuts.back() + minLayers);
+        c = std::min(c, gz - minLayers * (ranks - r));
+        cuts.push_back(c);
+    }
+    cuts.push_back(gz);
+    for (int r = 0; r < ranks; r++) if (cuts[r + 1] - cuts[r] < minLayers) return false;
+    return true;
+}
+
+// the sort half of a step: bounded scan, bucket, stable rank + gather, sorted ranges to the device words
+void enqueue_sort(MultiRank& r)
+{
+    sph_system* s = r.s;
+    sph_system::Slab& b = s->slab;
+    SphLaunch L = sph_launcher(s);
+    const int in = s->cur, outb = s->cur ^ 1, CL = b.numCellsLocal, yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+    uint32_t* st = s->counters;
+    sph_launch_slab_scan_bound(L, s->keyMax, 2u * (uint32_t)yx, CL);
+    sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL, s->keyMax + kKeyMaxSlots);
+    sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, r.capacity, st + SD_WORK);
+    sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS,
+                           r.capacity, st + SD_WORK);
+    const int lo = b.lowLayers;
+    const int cells[7] = {lo * yx, (lo + nz) * yx, CL, (lo + 1) * yx, (lo + nz - 1) * yx,
+                          (lo + std::min(2, nz)) * yx, (lo + std::max(nz - 2, 0)) * yx};
+    sph_launch_slab_bounds(L, s->cellStart, s->keyMax + kKeyMaxSlots, st, cells, b.hasLower, b.hasUpper);
+    s->cur = outb;
+}
+
+int check_flags(sph_multi* m, MultiRank& r)
+{
+    const uint32_t* h = r.hostSt;
+    r.owned = (int)(h[SD_END] - h[SD_FIRST]);
+    if (h[SD_OVERFLOW])
+        return mfail(m, SPH_ERR_STATE, "slab %d: exchange overflow -- a message section (%d leavers / %d boundary records) or the "
+                     "work set (%u of capacity %d) was too small", r.rank, m->capL, m->capB, h[SD_WORK], r.capacity);
+    if (h[SD_LOST])
+        return mfail(m, SPH_ERR_STATE, "slab %d: a particle moved more than one cell layer along z in a step; the slab "
+                     "decomposition cannot follow it (time step too large for the cell size?)", r.rank);
+    if (h[SD_DPERR])
+        return mfail(m, SPH_ERR_STATE, "slab %d: ghost sets out of step between neighbouring slabs", r.rank);
+    return SPH_OK;
+}
+
+int sync_rank(sph_multi* m, MultiRank& r)
+{
+    MCU(m, cudaSetDevice(r.device));
+    MCU(m, cudaMemcpyAsync(r.hostSt, r.s->counters, SD_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, r.s->stream));
+    MCU(m, cudaStreamSynchronize(r.s->stream));
+    MCU(m, cudaStreamSynchronize(r.xs));
+    return check_flags(m, r);
+}
+
+int create_common(sph_multi* m, const SimParams* p, int capacity)
+{
+    m->par = *p;
+    for (MultiRank& r : m->ranks) {
+        SimParams local = *p;
+        local.numParticles = (uint)capacity;
+        r.capacity = capacity;
+        sph_t* h = nullptr;
+        if (sph_create(&local, r.device, &h) != SPH_OK)
+            return mfail(m, SPH_ERR_CUDA, "sph_multi: slab %d on device %d: %s", r.rank, r.device, sph_last_error(nullptr));
+        r.s = h;
+        if (h->cfg.mode == SPH_PAIR_TMA)
+            return mfail(m, SPH_ERR_PARAMS, "sph_multi: the TMA-staged pair kernels have no device-resident ranges (use rm or l1)");
+        MCU(m, cudaSetDevice(r.device));
+        MCU(m, cudaStreamCreateWithFlags(&r.xs, cudaStreamNonBlocking));
+        cudaEvent_t* evs[] = {&r.evA, &r.evX1, &r.evDp, &r.evX2};
+        for (cudaEvent_t* e : evs) MCU(m, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        MCU(m, cudaMallocHost((void**)&r.hostSt, SD_WORDS * sizeof(uint32_t)));
+        memset(r.hostSt, 0, SD_WORDS * sizeof(uint32_t));
+    }
+    return SPH_OK;
+}
+
+// One nearest-neighbour exchange of every local slab on its exchange stream, after `ready` (recorded on the slab's solver
+// stream): out buffers go to the neighbours' in buffers.  NCCL: grouped ncclSend / ncclRecv.  Copy mode (one process):
+// each slab pulls from its neighbours once THEIR buffers are ready.
+template <class T>
+int exchange(sph_multi* m, size_t bytes, cudaEvent_t MultiRank::*ready, T* MultiRank::*pOutDown, T* MultiRank::*pOutUp,
+             T* MultiRank::*pInBelow, T* MultiRank::*pInAbove)
+{
+    auto outDown = [&](MultiRank& r) { return r.*pOutDown; };
+    auto outUp = [&](MultiRank& r) { return r.*pOutUp; };
+    auto inBelow = [&](MultiRank& r) { return r.*pInBelow; };
+    auto inAbove = [&](MultiRank& r) { return r.*pInAbove; };
+    if (m->copyExchange) {
+        for (MultiRank& r : m->ranks) {
+            MCU(m, cudaSetDevice(r.device));
+            if (r.hasLower) {
+                MultiRank& lo = m->ranks[r.rank - 1];
+                MCU(m, cudaStreamWaitEvent(r.xs, lo.*ready, 0));
+                MCU(m, cudaMemcpyPeerAsync(inBelow(r), r.device, outUp(lo), lo.device, bytes, r.xs));
+                m->bytesSent += bytes;
+            }
+            if (r.hasUpper) {
+                MultiRank& hi = m->ranks[r.rank + 1];
+                MCU(m, cudaStreamWaitEvent(r.xs, hi.*ready, 0));
+                MCU(m, cudaMemcpyPeerAsync(inAbove(r), r.device, outDown(hi), hi.device, bytes, r.xs));
+                m->bytesSent += bytes;
+            }
+        }
+        return SPH_OK;
+    }
+    MNCCL(m, g_nccl.GroupStart());
+    for (MultiRank& r : m->ranks) {
+        MCU(m, cudaSetDevice(r.device));
+        MCU(m, cudaStreamWaitEvent(r.xs, r.*ready, 0));
+        if (r.hasLower) {
+            MNCCL(m, g_nccl.Send(outDown(r), bytes, ncclChar, r.rank - 1, r.comm, r.xs));
+            MNCCL(m, g_nccl.Recv(inBelow(r), bytes, ncclChar, r.rank - 1, r.comm, r.xs));
+            m->bytesSent += bytes;
+        }
+        if (r.hasUpper) {
+            MNCCL(m, g_nccl.Send(outUp(r), bytes, ncclChar, r.rank + 1, r.comm, r.xs));
+            MNCCL(m, g_nccl.Recv(inAbove(r), bytes, ncclChar, r.rank + 1, r.comm, r.xs));
+            m->bytesSent += bytes;
+        }
+    }
+    MNCCL(m, g_nccl.GroupEnd());
+    return SPH_OK;
+}
+
+}  // namespace
+
+extern "C" const char* sph_multi_last_error(sph_multi_t* m) { return m ? m->err.c_str() : g_multiCreateError.c_str(); }
+
+extern "C" int sph_multi_unique_id(unsigned char* id128)
+{
+    std::string why;
+    if (!id128) return SPH_ERR_ARG;
+    if (!load_nccl(why)) return mfail(nullptr, SPH_ERR_CUDA, "sph_multi_unique_id: %s", why.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    MNCCL(nullptr, g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_destroy(sph_multi_t* m)
+{
+    if (!m) return SPH_ERR_ARG;
+    for (MultiRank& r : m->ranks) {
+        cudaSetDevice(r.device);
+        if (r.s && r.s->stream) cudaStreamSynchronize(r.s->stream);
+        if (r.xs) cudaStreamSynchronize(r.xs);
+        if (r.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(r.comm);
+        free_messages(r);
+        cudaEvent_t evs[] = {r.evA, r.evX1, r.evDp, r.evX2};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        if (r.xs) cudaStreamDestroy(r.xs);
+        if (r.hostSt) cudaFreeHost(r.hostSt);
+        if (r.s) sph_destroy(r.s);
+    }
+    delete m;
+    return SPH_OK;
+}
+
+// One process, ndev GPUs.  capacityPerSlab = particle slots of every slab (owned + ghosts + arrivals of a step).
+extern "C" int sph_multi_create(const struct SimParams* params, int ndev, const int* devices, int capacityPerSlab, sph_multi_t** out)
+{
+    if (!params || !out || ndev < 1 || !devices || capacityPerSlab < 1) return mfail(nullptr, SPH_ERR_ARG, "sph_multi_create: bad argument");
+    std::string why;
+    sph_multi* m = new sph_multi;
+    m->world = ndev;
+    m->ranks.resize(ndev);
+    for (int k = 0; k < ndev; k++) { m->ranks[k].device = devices[k];  m->ranks[k].rank = k; }
+    bool repeated = false;
+    for (int a = 0; a < ndev; a++) for (int b = a + 1; b < ndev; b++) repeated |= devices[a] == devices[b];
+    const char* xe = getenv("SPH_B200_MULTI_XCHG");          // "copy" | "nccl"
+    m->copyExchange = repeated || (xe && strcmp(xe, "copy") == 0);
+    if (ndev > 1 && !m->copyExchange && !load_nccl(why)) { delete m;  return mfail(nullptr, SPH_ERR_CUDA, "sph_multi_create: %s", why.c_str()); }
+    int rc = create_common(m, params, capacityPerSlab);
+    if (rc == SPH_OK && ndev > 1 && !m->copyExchange) {
+        std::vector<ncclComm_t> comms(ndev);
+        ncclResult_t r = g_nccl.CommInitAll(comms.data(), ndev, devices);
+        if (r != ncclSuccess) rc = mfail(m, SPH_ERR_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+        else for (int k = 0; k < ndev; k++) m->ranks[k].comm = comms[k];
+    }
+    if (rc != SPH_OK) { g_multiCreateError = m->err;  sph_multi_destroy(m);  return rc; }
+    *out = m;
+    return SPH_OK;
+}
+
+// One process per GPU: slab `rank` of `world`, communicator from a unique id every process received (sph_multi_unique_id
+// on one of them, distributed by whatever launched the job).
+extern "C" int sph_multi_create_rank(const struct SimParams* params, int rank, int world, const unsigned char* id128, int device,
+                                     int capacityPerSlab, sph_multi_t** out)
+{
+    if (!params || !out || world < 1 || rank < 0 || rank >= world || capacityPerSlab < 1 || (world > 1 && !id128))
+        return mfail(nullptr, SPH_ERR_ARG, "sph_multi_create_rank: bad argument");
+    std::string why;
+    if (world > 1 && !load_nccl(why)) return mfail(nullptr, SPH_ERR_CUDA, "sph_multi_create_rank: %s", why.c_str());
+    sph_multi* m = new sph_multi;
+    m->world = world;
+    m->ranks.resize(1);
+    m->ranks[0].device = device;  m->ranks[0].rank = rank;
+    int rc = create_common(m, params, capacityPerSlab);
+    if (rc == SPH_OK && world > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, 128);
+        cudaSetDevice(device);
+        ncclResult_t r = g_nccl.CommInitRank(&m->ranks[0].comm, world, id, rank);
+        if (r != ncclSuccess) rc = mfail(m, SPH_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    if (rc != SPH_OK) { g_multiCreateError = m->err;  sph_multi_destroy(m);  return rc; }
+    *out = m;
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_set_params(sph_multi_t* m, const struct SimParams* p)
+{
+    if (!m || !p) return SPH_ERR_ARG;
+    m->par = *p;
+    for (MultiRank& r : m->ranks) {
+        SimParams local = *p;
+        local.numParticles = (uint)r.capacity;
+        if (sph_set_params(r.s, &local) != SPH_OK) return mfail(m, SPH_ERR_PARAMS, "slab %d: %s", r.rank, sph_last_error(r.s));
+    }
+    return SPH_OK;
+}
+
+// The whole system from HOST arrays in original particle order (float4 rows; every process passes the same arrays).
+// cuts = world+1 z-layer boundaries, or NULL to balance the particle counts.  Each slab takes the particles of its layers,
+// sorts them once and is ready to step.
+extern "C" int sph_multi_set_state(sph_multi_t* m, const float* pos, const float* vel, int n, const int* cuts)
+{
+    if (!m || !pos || !vel || n < 1) return SPH_ERR_ARG;
+    const SimParams& P = m->par;
+    const int gz = (int)P.gridSize.z, W = m->world;
+    std::vector<int> zc(n);
+    std::vector<long long> hist(gz, 0);
+    for (int i = 0; i < n; i++) {
+        int z = host_z_cell(P, pos[4 * (size_t)i + 2]);
+        z = std::min(std::max(z, 0), gz - 1);
+        zc[i] = z;
+        hist[z]++;
+    }
+    if (cuts) m->cuts.assign(cuts, cuts + W + 1);
+    else if (!cut_layers(hist, W, 2, m->cuts)) return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: %d z layers are too few for %d slabs", gz, W);
+    if (m->cuts.front() != 0 || m->cuts.back() != gz) return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: cuts must run from 0 to gridSize.z");
+    for (int r = 0; r < W; r++) if (m->cuts[r + 1] - m->cuts[r] < 1) return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: empty slab %d", r);
+
+    // message sections from the fullest layer: every slab agrees on them (fixed-size messages, counts in the header row)
+    const long long fullest = *std::max_element(hist.begin(), hist.end());
+    const char* se = getenv("SPH_B200_SLAB_SAFETY");
+    const double safety = se ? atof(se) : 1.5;
+    // (a safety below 1 is a test aid: no slack, so that the overflow report can be exercised)
+    const int capB = (int)std::min<long long>(std::max<long long>((long long)(fullest * safety), 64) + (safety >= 1.0 ? 8192 : 0), 0x3fffffff);
+    const int capL = safety >= 1.0 ? std::max(capB / 4, 4096) : std::max(capB / 4, 16);
+    const bool resize = capB != m->capB || capL != m->capL;
+    m->capB = capB;  m->capL = capL;
+
+    std::vector<float> rec;
+    for (MultiRank& r : m->ranks) {
+        sph_system* s = r.s;
+        MCU(m, cudaSetDevice(r.device));
+        r.zLo = m->cuts[r.rank];  r.zHi = m->cuts[r.rank + 1];
+        r.hasLower = r.rank > 0;  r.hasUpper = r.rank < W - 1;
+        if (sph_slab_configure(s, r.zLo, r.zHi, r.hasLower, r.hasUpper) != SPH_OK)
+            return mfail(m, SPH_ERR_PARAMS, "slab %d: %s", r.rank, sph_last_error(s));
+        if (resize || !r.msgDown) if (int rc = alloc_messages(m, r)) return rc;
+        long long mine = 0;
+        for (int z = r.zLo; z < r.zHi; z++) mine += hist[z];
+        if (mine + 2LL * capB + 2LL * capL > r.capacity)
+            return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: slab %d owns %lld particles; with ghosts and arrivals that exceeds its "
+                         "capacity of %d slots", r.rank, mine, r.capacity);
+        rec.resize((size_t)std::max<long long>(mine, 1) * kRecFloats);
+        size_t k = 0;
+        for (int i = 0; i < n; i++) {
+            if (zc[i] < r.zLo || zc[i] >= r.zHi) continue;
+            float* o = rec.data() + k * kRecFloats;
+            memcpy(o, pos + 4 * (size_t)i, 16);
+            memcpy(o + 4, vel + 4 * (size_t)i, 16);
+            const uint32_t id = (uint32_t)i;
+            memcpy(o + 8, &id, 4);
+            o[9] = o[10] = o[11] = 0.f;
+            k++;
+        }
+        // staged through the list buffer (192 bytes per slot, rebuilt by every step)
+        float* stage = reinterpret_cast<float*>(s->nlist);
+        MCU(m, cudaMemcpyAsync(stage, rec.data(), (size_t)mine * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        if (sph_slab_set_owned(s, stage, (int)mine) != SPH_OK) return mfail(m, SPH_ERR_CUDA, "slab %d: %s", r.rank, sph_last_error(s));
+        // device words: the work set is the owned particles, nothing sorted yet; then one sort without integration
+        uint32_t st[SD_WORDS] = {};
+        st[SD_WORK] = st[SD_WORK0] = st[SD_END] = st[SD_G2] = (uint32_t)mine;
+        st[SD_BLO] = st[SD_BLO2] = 0;  st[SD_BHI] = st[SD_BHI2] = (uint32_t)mine;
+        memcpy(r.hostSt, st, sizeof st);
+        MCU(m, cudaMemcpyAsync(s->counters, r.hostSt, sizeof st, cudaMemcpyHostToDevice, s->stream));
+        sph_system::Slab& b = s->slab;
+        const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+        sph_launch_slab_interior_hist(sph_launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->keyU, s->rankU, s->cellCount,
+                                      s->counters, r.capacity, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
+                                      (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 0);
+        enqueue_sort(r);
+        // the gather put the sorted velocities into velS (where a step's force kernel reads them); the live array is vel
+        MCU(m, cudaMemcpyAsync(s->vel, s->velS, (size_t)r.capacity * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        MCU(m, cudaGetLastError());
+        MCU(m, cudaStreamSynchronize(s->stream));
+        s->stepped = false;
+        r.owned = (int)mine;
+    }
+    m->haveState = true;
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
+{
+    if (!m || nsteps < 0) return SPH_ERR_ARG;
+    if (!m->haveState) return mfail(m, SPH_ERR_STATE, "sph_multi_step: call sph_multi_set_state first");
+    const int capL = m->capL, capB = m->capB;
+    const bool multi = m->world > 1;
+    for (int step = 0; step < nsteps; step++) {
+        // ---- A: edge layers + particle messages; B: everything else, overlapping exchange 1
+        for (MultiRank& r : m->ranks) {
+            sph_system* s = r.s;
+            sph_system::Slab& b = s->slab;
+            MCU(m, cudaSetDevice(r.device));
+            SphLaunch L = sph_launcher(s);
+            const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+            if (m->copyExchange && multi) {
+                // the neighbours pulled this slab's out buffers on THEIR exchange streams: wait for last step's pulls
+                if (r.hasLower) { MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX1, 0));  MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX2, 0)); }
+                if (r.hasUpper) { MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evX1, 0));  MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evX2, 0)); }
+            }
+            MCU(m, cudaMemsetAsync(r.msgDown, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+            MCU(m, cudaMemsetAsync(r.msgUp, 0, SPH_SLAB_RECORD_BYTES, s->stream));
+            if (multi) {
+                // thin slabs: the two edge regions are the whole slab
+                const long long boundA = nz < 4 ? (long long)r.capacity : std::min<long long>(r.capacity, 4LL * capB);
+                sph_launch_slab_boundary_integrate_pack(L, s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->counters, (int)boundA,
+                                                        b.zLo, b.zHi, b.hasLower, b.hasUpper,
+                                                        r.msgDown + kRecFloats, r.msgUp + kRecFloats, capL,
+                                                        r.msgDown + (size_t)kRecFloats * (1 + capL), r.msgUp + (size_t)kRecFloats * (1 + capL), capB,
+                                                        reinterpret_cast<uint32_t*>(r.msgDown), reinterpret_cast<uint32_t*>(r.msgUp));
+                MCU(m, cudaEventRecord(r.evA, s->stream));
+            }
+            sph_launch_slab_interior_hist(L, s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->keyU, s->rankU, s->cellCount,
+                                          s->counters, r.capacity, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
+                                          (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 1);
+        }
+        if (multi)
+            if (int rc = exchange(m, msg_bytes(m), &MultiRank::evA, &MultiRank::msgDown, &MultiRank::msgUp, &MultiRank::inBelow, &MultiRank::inAbove)) return rc;
+        // ---- arrivals + ghosts, sort, density, rho,p rows
+        for (MultiRank& r : m->ranks) {
+            sph_system* s = r.s;
+            sph_system::Slab& b = s->slab;
+            MCU(m, cudaSetDevice(r.device));
+            SphLaunch L = sph_launcher(s);
+            const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+            if (multi) {
+                MCU(m, cudaEventRecord(r.evX1, r.xs));
+                MCU(m, cudaStreamWaitEvent(s->stream, r.evX1, 0));
+                sph_launch_slab_unpack_hist(L, s->par, r.hasLower ? r.inBelow : nullptr, r.hasUpper ? r.inAbove : nullptr,
+                                            r.hasLower ? r.msgDown : nullptr, r.hasUpper ? r.msgUp : nullptr, capL, capB,
+                                            s->pos[s->cur], s->vel, s->idx[s->cur], r.capacity, s->keyU, s->rankU, s->cellCount,
+                                            s->counters, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
+                                            (uint32_t)((b.lowLayers + nz) * yx), s->keyMax);
+            }
+            enqueue_sort(r);
+            const uint32_t* dev = s->counters + SD_FIRST;
+            if (s->timing) cudaEventRecord(s->ev[3], s->stream);
+            sph_launch_density(L, s->cfg, b.parLocal, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount, s->posP, s->velD,
+                               s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, r.capacity, dev);
+            if (s->timing) cudaEventRecord(s->ev[4], s->stream);
+            if (multi) {
+                sph_launch_slab_pack_dp(L, s->posP, s->velD, s->counters, r.dpDown, r.dpUp, capB);
+                MCU(m, cudaEventRecord(r.evDp, s->stream));
+            }
+        }
+        if (multi)
+            if (int rc = exchange(m, dp_bytes(m), &MultiRank::evDp, &MultiRank::dpDown, &MultiRank::dpUp, &MultiRank::dpBelow, &MultiRank::dpAbove)) return rc;
+        // ---- force: CTAs without ghost neighbours while the rows travel, then the rest
+        for (MultiRank& r : m->ranks) {
+            sph_system* s = r.s;
+            sph_system::Slab& b = s->slab;
+            MCU(m, cudaSetDevice(r.device));
+            SphLaunch L = sph_launcher(s);
+            const uint32_t* dev = s->counters + SD_FIRST;
+            if (s->timing) cudaEventRecord(s->evForce[0], s->stream);
+            auto force = [&](int part) {
+                sph_launch_force(L, s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount, s->nlist, s->ncount,
+                                 s->ctaRows, s->vel, 0, r.capacity, 0, -1, dev, part);
+            };
+            if (multi) {
+                MCU(m, cudaEventRecord(r.evX2, r.xs));
+                force(1);
+                MCU(m, cudaStreamWaitEvent(s->stream, r.evX2, 0));
+                sph_launch_slab_unpack_dp(L, r.hasLower ? r.dpBelow : nullptr, r.hasUpper ? r.dpAbove : nullptr, s->counters, s->posP, s->velD, capB);
+                force(2);
+            } else force(0);
+            if (sph_needs_obstacles(s->par)) sph_launch_obstacles(L, b.parLocal, s->posP, s->velD, s->vel, 0, r.capacity, dev);
+            if (s->timing) cudaEventRecord(s->evForce[1], s->stream);
+            s->stepped = true;
+            MCU(m, cudaGetLastError());
+        }
+        m->steps++;
+    }
+    return SPH_OK;
+}
+
+// waits for everything enqueued and reports what the device flagged (message overflow, lost particles, ghost mismatch)
+extern "C" int sph_multi_sync(sph_multi_t* m)
+{
+    if (!m) return SPH_ERR_ARG;
+    for (MultiRank& r : m->ranks) if (int rc = sync_rank(m, r)) return rc;
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_local_slabs(sph_multi_t* m) { return m ? (int)m->ranks.size() : 0; }
+extern "C" sph_t* sph_multi_handle(sph_multi_t* m, int local) { return m && local >= 0 && local < (int)m->ranks.size() ? m->ranks[local].s : nullptr; }
+extern "C" void* sph_multi_stream(sph_multi_t* m, int local) { sph_t* s = sph_multi_handle(m, local);  return s ? (void*)s->stream : nullptr; }
+
+// {z cuts[world+1]}, {owned particles of every LOCAL slab}, message geometry and traffic; any pointer may be NULL
+extern "C" int sph_multi_info(sph_multi_t* m, int* cuts, int* ownedLocal, int* capLB2, unsigned long long* bytesSent)
+{
+    if (!m) return SPH_ERR_ARG;
+    if (ownedLocal) { if (int rc = sph_multi_sync(m)) return rc; }
+    if (cuts) for (size_t k = 0; k < m->cuts.size(); k++) cuts[k] = m->cuts[k];
+    if (ownedLocal) for (size_t k = 0; k < m->ranks.size(); k++) ownedLocal[k] = m->ranks[k].owned;
+    if (capLB2) { capLB2[0] = m->capL;  capLB2[1] = m->capB; }
+    if (bytesSent) *bytesSent = m->bytesSent;
+    return SPH_OK;
+}
+
+// Owned particles of the local slabs into HOST arrays addressed by original particle index (rows of particles owned by
+// other processes are left untouched).  pos / vel: float4 rows; dens / pres: one float per particle; any may be NULL.
+extern "C" int sph_multi_get_state(sph_multi_t* m, float* pos, float* vel, float* dens, float* pres, int n, int* written)
+{
+    if (!m) return SPH_ERR_ARG;
+    if (!m->haveState) return mfail(m, SPH_ERR_STATE, "sph_multi_get_state: no state");
+    int total = 0;
+    std::vector<float> rec;
+    for (MultiRank& r : m->ranks) {
+        if (int rc = sync_rank(m, r)) return rc;
+        sph_system* s = r.s;
+        const int first = (int)r.hostSt[SD_FIRST], count = (int)(r.hostSt[SD_END] - r.hostSt[SD_FIRST]);
+        if (count <= 0) continue;
+        float* stage = reinterpret_cast<float*>(s->nlist);
+        sph_launch_slab_export(sph_launcher(s), s->pos[s->cur], s->vel, s->idx[s->cur], s->stepped ? s->posP : nullptr,
+                               s->stepped ? s->velD : nullptr, first, count, stage);
+        rec.resize((size_t)count * kRecFloats);
+        MCU(m, cudaMemcpyAsync(rec.data(), stage, rec.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        MCU(m, cudaStreamSynchronize(s->stream));
+        for (int k = 0; k < count; k++) {
+            const float* o = rec.data() + (size_t)k * kRecFloats;
+            uint32_t id;
+            memcpy(&id, o + 8, 4);
+            if (id >= (uint32_t)n) return mfail(m, SPH_ERR_STATE, "slab %d: record %d carries particle id %u >= %d", r.rank, k, id, n);
+            if (pos) memcpy(pos + 4 * (size_t)id, o, 16);
+            if (vel) memcpy(vel + 4 * (size_t)id, o + 4, 16);
+            if (dens) dens[id] = o[9];
+            if (pres) pres[id] = o[10];
+        }
+        total += count;
+    }
+    if (written) *written = total;
+    return SPH_OK;
+}

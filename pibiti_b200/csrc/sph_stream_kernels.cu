@@ -691,8 +691,10 @@ __global__ void k_slab_scan_bound(uint32_t* __restrict__ keyMaxSlots, uint32_t g
 // host used to read back after every sort live in the state words st[] (SlabDevWord, sph_device.cuh); kernels are
 // launched over upper bounds and find their own ranges, so a step never synchronises with the host.
 
-// Phase A: integrate the first and the last owned layer only and pack what the neighbours need from them (leavers, copies
-// of the boundary layers).  Thread t < nLo handles slot first + t, the next nHi threads the slots from bHi on.
+// Phase A: integrate the first two and the last two owned layers only -- a particle moves at most one layer per step, so
+// these are all that can leave the slab or land in a boundary layer -- and pack what the neighbours need from them
+// (leavers, copies of the boundary layers).  Thread t < nLo handles slot first + t, the next nHi threads the slots from
+// bHi on.
 __global__ void __launch_bounds__(256)
 k_slab_boundary_integrate_pack(const __grid_constant__ SimParams par, const BoundaryCtx ctx, float4* __restrict__ pos,
                                float4* __restrict__ vel, uint32_t* __restrict__ idx, uint32_t* __restrict__ st,
@@ -702,9 +704,9 @@ k_slab_boundary_integrate_pack(const __grid_constant__ SimParams par, const Boun
                                uint32_t* __restrict__ headDown, uint32_t* __restrict__ headUp)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO], bHi = st[SD_BHI];
+    const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO2], bHi = st[SD_BHI2];
     const uint32_t nLo = bLo - g0, nHi = g1 - bHi;
-    // the launch covers 2 * capB slots; a fuller layer does not fit the message either
+    // the launch is sized for layers that fit the messages; fuller ones do not fit the messages either
     if (t == 0 && nLo + nHi > gridDim.x * blockDim.x) st[SD_OVERFLOW] = 1u;
     const bool active = t < nLo + nHi;
     const uint32_t i = t < nLo ? g0 + t : bHi + (t - nLo);
@@ -763,11 +765,13 @@ k_slab_interior_hist(const __grid_constant__ SimParams par, const BoundaryCtx ct
     if (threadIdx.x == 0) blockMax = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t work = st[SD_WORK];
-    if (i == 0) st[SD_WORK0] = work;            // the unpack kernel appends behind this
+    // the work set of this step starts as [0, end of the owned range): the slots behind it (last step's ghosts above and
+    // retired slots, all sorted to the back) are dropped, so the work set does not grow from step to step
+    const uint32_t work = st[SD_END];
+    if (i == 0) { st[SD_WORK0] = work;  st[SD_WORK] = work; }       // the unpack kernel appends behind this
     uint32_t live1 = 0;
     if (i < work) {
-        const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO], bHi = st[SD_BHI];
+        const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO2], bHi = st[SD_BHI2];
         const bool owned = i >= g0 && i < g1;
         uint32_t id = idx[i];
         if (!owned && id != kDeadIndex) { idx[i] = kDeadIndex;  id = kDeadIndex; }
@@ -849,17 +853,19 @@ k_slab_unpack_hist(const __grid_constant__ SimParams par, const SlabRecord* __re
 // entries.  Entries at or above the scan bound were not written this step: no live key is that large, so they equal the
 // live total, which is the start of the dummy cell (always scanned).
 __global__ void k_slab_bounds(const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ scanBound, uint32_t* __restrict__ st,
-                              int c0, int c1, int c2, int c3, int c4, int hasLower, int hasUpper)
+                              int c0, int c1, int c2, int c3, int c4, int c5, int c6, int hasLower, int hasUpper)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int cells[5] = {c0, c1, c2, c3, c4};
+    const int cells[7] = {c0, c1, c2, c3, c4, c5, c6};
     const int bound = (int)*scanBound, lastTileStart = c2 / SPH_SCAN_TILE * SPH_SCAN_TILE;
-    uint32_t v[5];
+    uint32_t v[7];
     const uint32_t total = cellStart[c2];
-    for (int k = 0; k < 5; k++) v[k] = (cells[k] >= bound && cells[k] < lastTileStart) ? total : cellStart[cells[k]];
+    for (int k = 0; k < 7; k++) v[k] = (cells[k] >= bound && cells[k] < lastTileStart) ? total : cellStart[cells[k]];
     st[SD_FIRST] = v[0];  st[SD_END] = v[1];  st[SD_G2] = v[2];
     st[SD_BLO] = hasLower ? v[3] : v[0];        // no neighbour on a side: no boundary layer there
     st[SD_BHI] = hasUpper ? v[4] : v[1];
+    st[SD_BLO2] = hasLower ? v[5] : v[0];       // cells c5 / c6: two layers in from each end (the host clamps them to
+    st[SD_BHI2] = hasUpper ? max(v[6], st[SD_BLO2]) : v[1];      // the owned range when the slab is thinner than that)
 }
 
 // rho,p rows of the two boundary layers: [0] = {count, 0, 0, 0}, then (x,y,z,p), (vx,vy,vz,rho) per particle
@@ -1046,13 +1052,12 @@ void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void*
 
 // ---- slab mode, device-resident bookkeeping -------------------------------------------------------
 void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
-                                             uint32_t* st, int zLo, int zHi, int hasLower, int hasUpper,
+                                             uint32_t* st, int bound, int zLo, int zHi, int hasLower, int hasUpper,
                                              void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
                                              uint32_t* headDown, uint32_t* headUp)
 {
     const BoundaryCtx ctx = boundary_ctx(par);
-    // a boundary layer holds at most capB particles (more would overflow the message anyway)
-    k_slab_boundary_integrate_pack<<<blocks_for(2 * capB, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, st, zLo, zHi, hasLower, hasUpper,
+    k_slab_boundary_integrate_pack<<<blocks_for(bound, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, st, zLo, zHi, hasLower, hasUpper,
                                                                                   (SlabRecord*)leavDown, (SlabRecord*)leavUp, capL,
                                                                                   (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp);
     SPH_COUNT(L);
@@ -1089,9 +1094,10 @@ void sph_launch_slab_scan_bound(const SphLaunch& L, uint32_t* keyMaxSlots, uint3
 }
 
 void sph_launch_slab_bounds(const SphLaunch& L, const uint32_t* cellStart, const uint32_t* scanBound, uint32_t* st,
-                            const int cells[5], int hasLower, int hasUpper)
+                            const int cells[7], int hasLower, int hasUpper)
 {
-    k_slab_bounds<<<1, 32, 0, L.stream>>>(cellStart, scanBound, st, cells[0], cells[1], cells[2], cells[3], cells[4], hasLower, hasUpper);
+    k_slab_bounds<<<1, 32, 0, L.stream>>>(cellStart, scanBound, st, cells[0], cells[1], cells[2], cells[3], cells[4], cells[5], cells[6],
+                                          hasLower, hasUpper);
     SPH_COUNT(L);
 }
 

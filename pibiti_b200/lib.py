@@ -85,6 +85,9 @@ ABI_SYMBOLS = (
     "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack", "sph_slab_integrate_pack",
     "sph_slab_unpack", "sph_slab_sort", "sph_slab_density", "sph_slab_pack_dp", "sph_slab_ghost_counts",
     "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_force_part", "sph_slab_stats",
+    "sph_multi_unique_id", "sph_multi_create", "sph_multi_create_rank", "sph_multi_destroy", "sph_multi_last_error",
+    "sph_multi_set_params", "sph_multi_set_state", "sph_multi_step", "sph_multi_sync", "sph_multi_get_state",
+    "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info",
 )
 
 
@@ -147,6 +150,23 @@ def load() -> C.CDLL:
     lib.sph_slab_force_part.argtypes = [vp, ci]
     lib.sph_slab_integrate_pack.argtypes = [vp, vp, vp, ci, ci]
     lib.sph_slab_stats.argtypes = [vp, ip]
+    lib.sph_multi_unique_id.argtypes = [vp]
+    lib.sph_multi_create.argtypes = [vp, ci, ip, ci, C.POINTER(vp)]
+    lib.sph_multi_create_rank.argtypes = [vp, ci, ci, vp, ci, ci, C.POINTER(vp)]
+    lib.sph_multi_destroy.argtypes = [vp]
+    lib.sph_multi_last_error.argtypes = [vp]
+    lib.sph_multi_last_error.restype = C.c_char_p
+    lib.sph_multi_set_params.argtypes = [vp, vp]
+    lib.sph_multi_set_state.argtypes = [vp, vp, vp, ci, ip]
+    lib.sph_multi_step.argtypes = [vp, ci]
+    lib.sph_multi_sync.argtypes = [vp]
+    lib.sph_multi_get_state.argtypes = [vp, vp, vp, vp, vp, ci, ip]
+    lib.sph_multi_local_slabs.argtypes = [vp]
+    lib.sph_multi_handle.argtypes = [vp, ci]
+    lib.sph_multi_handle.restype = vp
+    lib.sph_multi_stream.argtypes = [vp, ci]
+    lib.sph_multi_stream.restype = vp
+    lib.sph_multi_info.argtypes = [vp, ip, ip, ip, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
 
@@ -250,3 +270,112 @@ class SphSystem:
         p, v, i, cs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self.lib.sph_device_buffers(self.h, C.byref(p), C.byref(v), C.byref(i), C.byref(cs)), "sph_device_buffers")
         return p.value, v.value, i.value, cs.value
+
+
+class _SlabView(SphSystem):
+    """One slab of a MultiSystem as an SphSystem (timings, launch counts, dumps); the handle stays owned by the driver."""
+
+    def __init__(self, lib, handle, params):  # noqa: super().__init__ deliberately not called
+        self.lib, self.h = lib, C.c_void_p(handle)
+        self.params = params_array(params.tobytes())
+        self.n = int(self.params["numParticles"][0])
+        self.num_cells = int(self.params["numCells"][0])
+
+    def close(self):
+        self.h = C.c_void_p()
+
+
+class MultiSystem:
+    """ctypes wrapper over sph_multi_* (include/sph_b200.h): the whole system on several GPUs, z-slab decomposed, driven by
+    the C++ multi-GPU driver (NCCL send/recv or peer copies between the slabs).  Either `devices` (one process drives them
+    all) or `rank`/`world`/`unique_id`/`device` (one process per GPU)."""
+
+    def __init__(self, params: np.ndarray, capacity_per_slab: int, devices=None, rank=None, world=None, unique_id: bytes | None = None,
+                 device: int = 0):
+        self.lib = load()
+        self.params = params_array(params.tobytes())
+        self.h = C.c_void_p()
+        self.capacity = int(capacity_per_slab)
+        if devices is not None:
+            self.world = len(devices)
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.sph_multi_create(_ptr(self.params), len(devices), arr, self.capacity, C.byref(self.h))
+        else:
+            self.world = int(world)
+            buf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+            rc = self.lib.sph_multi_create_rank(_ptr(self.params), int(rank), int(world), buf, int(device), self.capacity, C.byref(self.h))
+        if rc != 0:
+            raise SphError(f"sph_multi_create failed ({rc}): {self.lib.sph_multi_last_error(None).decode()}")
+        self.n = 0
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = load()
+        buf = (C.c_ubyte * 128)()
+        if lib.sph_multi_unique_id(buf) != 0:
+            raise SphError("sph_multi_unique_id failed: " + lib.sph_multi_last_error(None).decode())
+        return bytes(buf)
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise SphError(f"{what} failed ({rc}): {self.lib.sph_multi_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.sph_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params: np.ndarray):
+        self.params = params_array(params.tobytes())
+        self._check(self.lib.sph_multi_set_params(self.h, _ptr(self.params)), "sph_multi_set_params")
+
+    def set_state(self, pos: np.ndarray, vel: np.ndarray, cuts=None):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 4)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 4)
+        assert pos.shape == vel.shape
+        c = (C.c_int * (self.world + 1))(*cuts) if cuts is not None else None
+        self.n = pos.shape[0]
+        self._check(self.lib.sph_multi_set_state(self.h, _ptr(pos), _ptr(vel), self.n, c), "sph_multi_set_state")
+
+    def step(self, nsteps: int = 1):
+        self._check(self.lib.sph_multi_step(self.h, nsteps), "sph_multi_step")
+
+    def sync(self):
+        self._check(self.lib.sph_multi_sync(self.h), "sph_multi_sync")
+
+    def get_state(self, density: bool = False):
+        """(pos, vel[, dens, pres], written): rows of particles this process does not own stay NaN."""
+        n = self.n
+        pos, vel = np.full((n, 4), np.nan, np.float32), np.full((n, 4), np.nan, np.float32)
+        dens = np.full(n, np.nan, np.float32) if density else None
+        pres = np.full(n, np.nan, np.float32) if density else None
+        w = C.c_int(0)
+        self._check(self.lib.sph_multi_get_state(self.h, _ptr(pos), _ptr(vel), _ptr(dens) if density else None,
+                                                 _ptr(pres) if density else None, n, C.byref(w)), "sph_multi_get_state")
+        return (pos, vel, dens, pres, w.value) if density else (pos, vel, w.value)
+
+    def local_slabs(self) -> int:
+        return int(self.lib.sph_multi_local_slabs(self.h))
+
+    def slab(self, local: int = 0) -> _SlabView:
+        par = self.params.copy()
+        par["numParticles"] = self.capacity
+        return _SlabView(self.lib, self.lib.sph_multi_handle(self.h, local), par)
+
+    def stream(self, local: int = 0) -> int:
+        return int(self.lib.sph_multi_stream(self.h, local) or 0)
+
+    def info(self, owned: bool = True) -> dict:
+        cuts = (C.c_int * (self.world + 1))()
+        own = (C.c_int * max(self.local_slabs(), 1))()
+        caps = (C.c_int * 2)()
+        sent = C.c_ulonglong(0)
+        self._check(self.lib.sph_multi_info(self.h, cuts, own if owned else None, caps, C.byref(sent)), "sph_multi_info")
+        return {"cuts": list(cuts), "owned": list(own)[: self.local_slabs()] if owned else None, "cap_leavers": caps[0],
+                "cap_boundary": caps[1], "bytes_sent": int(sent.value)}

@@ -1,0 +1,127 @@
+"""The C++ multi-GPU driver (sph_multi_*, pibiti_b200/csrc/sph_multi.cu): a run cut into R z slabs must equal the
+single-GPU run bit for bit -- positions, velocities and densities -- with particles stirred along z so that they migrate
+between slabs.  On a one-GPU box all slabs share cuda:0 (the driver then copies the neighbours' buffers directly instead
+of calling NCCL); tests/multi_worker.py runs the one-process-per-GPU shape over NCCL where two GPUs are visible."""
+from __future__ import annotations
+
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from pibiti_b200 import host, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def stir(vel):
+    v = vel.copy()
+    v[:, 2] = 1.5 * np.sin(np.arange(v.shape[0], dtype=np.float32) * np.float32(0.37)).astype(np.float32)
+    return v
+
+
+def single_gpu_run(title, steps):
+    s = host.CSph(device=0)
+    s.select_scene(title)
+    g = s.solver()
+    g.set_array(lib.SPH_VEL, stir(s.host_arrays()[1]))
+    for _ in range(steps):
+        s.UpdateEmitter()
+        s.Update()
+    out = g.get_array(lib.SPH_POS), g.get_array(lib.SPH_VEL), g.get_array(lib.SPH_DENSITY)
+    s.close()
+    return out
+
+
+def multi_run(title, steps, slabs, monkeypatch=None, variant=None, check_every=0):
+    s = host.CSph(device=-1)                      # scene + initial state on the host only
+    s.select_scene(title)
+    par = s.params
+    pos, vel = s.host_arrays()
+    vel = stir(vel)
+    n = s.n
+    m = lib.MultiSystem(par, capacity_per_slab=int(n / slabs * 1.6) + 40000, devices=[0] * slabs)
+    m.set_state(pos, vel)
+    owned0 = m.info()["owned"]
+    assert sum(owned0) == n
+    for k in range(steps):
+        s.UpdateEmitter()
+        m.set_params(s.params)
+        m.step(1)
+        if check_every and (k + 1) % check_every == 0:
+            m.sync()
+    p, v, d, _, written = m.get_state(density=True)
+    info = m.info()
+    m.close()
+    assert written == n and sum(info["owned"]) == n
+    return (p, v, d), owned0, info
+
+
+@pytest.mark.parametrize("title,slabs", [("mini waves", 2), ("mini waves", 3), ("wave tank 256k", 4), ("mini box", 1)])
+def test_multi_driver_equals_single_gpu(title, slabs):
+    steps = 10
+    got, owned0, info = multi_run(title, steps, slabs)
+    ref = single_gpu_run(title, steps)
+    for a, b, what in zip(got, ref, ("positions", "velocities", "densities")):
+        assert np.array_equal(a, b), f"{what} differ"
+    if slabs > 1 and "waves" in title:
+        assert info["owned"] != owned0, "the test should exercise migration between slabs"
+        assert info["bytes_sent"] > 0
+
+
+@pytest.mark.parametrize("variant", ["l1,128,1344,48", "rm,64,24,48"])
+def test_multi_driver_other_pair_variants(monkeypatch, variant):
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", variant)
+    got, _, _ = multi_run("mini waves", 6, 3)
+    ref = single_gpu_run("mini waves", 6)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+def test_multi_driver_reports_message_overflow(monkeypatch):
+    """Sections sized far below a layer's population: the device flags it and the next sync reports it."""
+    monkeypatch.setenv("SPH_B200_SLAB_SAFETY", "0.01")
+    s = host.CSph(device=-1)
+    s.select_scene("wave tank 256k")
+    pos, vel = s.host_arrays()
+    m = lib.MultiSystem(s.params, capacity_per_slab=s.n, devices=[0, 0])
+    m.set_state(pos, stir(vel))
+    m.step(2)
+    with pytest.raises(lib.SphError, match="overflow"):
+        m.sync()
+    m.close()
+
+
+def test_multi_driver_rejects_unsupported_boundaries():
+    s = host.CSph(device=-1)
+    s.select_scene("mini pump square")
+    m = lib.MultiSystem(s.params, capacity_per_slab=s.n, devices=[0, 0])
+    pos, vel = s.host_arrays()
+    with pytest.raises(lib.SphError, match="pump"):
+        m.set_state(pos, vel)
+    m.close()
+
+
+def free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_multi_driver_nccl_two_processes(tmp_path):
+    """One process per GPU over ncclSend/ncclRecv (the shape bench.py runs under torchrun); needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = tmp_path / "multi.npz"
+    steps = 8
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), str(ROOT / "tests" / "multi_worker.py"), "wave tank 256k", str(steps), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = np.load(out)
+    ref = single_gpu_run("wave tank 256k", steps)
+    assert np.array_equal(got["pos"], ref[0]) and np.array_equal(got["vel"], ref[1]) and np.array_equal(got["dens"], ref[2])
