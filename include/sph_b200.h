@@ -201,6 +201,15 @@ int sph_multi_sync(sph_multi_t* m);
 /* cSPH::getArray: owned particles of this process's slabs into HOST arrays indexed by original particle id (float4 rows
  * for pos / vel, one float for dens / pres; NULL to skip).  Rows owned by other processes are left untouched. */
 int sph_multi_get_state(sph_multi_t* m, float* pos, float* vel, float* dens, float* pres, int n, int* written);
+/* The owned particles of one LOCAL slab as 48-byte records {pos xyzw, vel xyzw, (original index, rho, p, 0)} to / from HOST
+ * memory: the per-process accessor of the one-process-per-GPU shape (no scan of the whole system).  put expects records
+ * that lie in the slab's layers (what fetch returned, possibly modified). */
+int sph_multi_fetch_owned(sph_multi_t* m, int local, float* hostRecords, int capacityRecords, int* count);
+int sph_multi_put_owned(sph_multi_t* m, int local, const float* hostRecords, int count);
+/* phase profile of the last step of a local slab, ms on its solver stream: {edge integrate + pack, interior integrate +
+ * histogram, wait for the particle exchange, unpack arrivals, scan + bucket + gather, density, pack rho/p rows, interior
+ * force, wait for the rho/p exchange, unpack rho/p rows, boundary force}; enable it first */
+int sph_multi_phase_ms(sph_multi_t* m, int local, int enable, float* out11);
 int sph_multi_local_slabs(sph_multi_t* m);
 sph_t* sph_multi_handle(sph_multi_t* m, int local);                             /* timings, dumps, launch counts of one slab */
 void* sph_multi_stream(sph_multi_t* m, int local);                              /* cudaStream_t the slab's kernels run on */

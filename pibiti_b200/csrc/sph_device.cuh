@@ -137,7 +137,8 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
                       const uint32_t* ctaRows, float4* velOut, int first, int count,
                       int ctaFirst = 0, int ctaCount = -1 /* L1 / rm variants: only CTAs [ctaFirst, ctaFirst+ctaCount) of the range */,
-                      const uint32_t* dev = nullptr, int part = 0 /* with dev: 1 = CTAs without ghost neighbours, 2 = the others */);
+                      const uint32_t* dev = nullptr, int part = 0 /* with dev: 1 = CTAs without ghost neighbours, 2 = the others */,
+                      int part2Blocks = 0 /* part 2: CTAs to launch (an upper bound of those that touch the two boundary layers) */);
 
 // ---- sph_extras_kernels.cu --------------------------------------------------------------------
 bool sph_needs_obstacles(const SimParams& par);        // height map or rotor configured

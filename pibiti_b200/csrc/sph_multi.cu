@@ -83,6 +83,7 @@ struct MultiRank {
     float *msgDown = nullptr, *msgUp = nullptr, *inBelow = nullptr, *inAbove = nullptr;      // particle messages
     float4 *dpDown = nullptr, *dpUp = nullptr, *dpBelow = nullptr, *dpAbove = nullptr;       // rho,p rows
     cudaEvent_t evA = nullptr, evX1 = nullptr, evDp = nullptr, evX2 = nullptr;
+    cudaEvent_t evPhase[12] = {};               // phase profile of the last step (sph_multi_phase_ms)
     uint32_t* hostSt = nullptr;                 // pinned copy of the device words
     int owned = 0;                              // as of the last sph_multi_sync / set_state
 };
@@ -96,6 +97,7 @@ struct sph_multi {
     SimParams par;                              // global parameters (numParticles = particles of the whole system)
     int capL = 0, capB = 0;                     // message sections: leavers, boundary-layer copies (records)
     bool haveState = false;
+    bool phaseTiming = false;                   // record the phase events (a handful of event records per step)
     bool copyExchange = false;                  // one process: neighbours' buffers are copied directly (cudaMemcpyPeerAsync)
                                                 // instead of ncclSend/ncclRecv -- also what lets several slabs share one GPU
     long long steps = 0;
@@ -219,6 +221,32 @@ int sync_rank(sph_multi* m, MultiRank& r)
     return check_flags(m, r);
 }
 
+// `count` particle records staged on the device become the slab's owned set: one sort without integration establishes
+// the sorted ranges the first step's edge-layer pass needs
+int load_slab(sph_multi* m, MultiRank& r, const float* d_records, int count)
+{
+    sph_system* s = r.s;
+    if (sph_slab_set_owned(s, d_records, count) != SPH_OK) return mfail(m, SPH_ERR_CUDA, "slab %d: %s", r.rank, sph_last_error(s));
+    uint32_t st[SD_WORDS] = {};
+    st[SD_WORK] = st[SD_WORK0] = st[SD_END] = st[SD_G2] = (uint32_t)count;
+    st[SD_BLO] = st[SD_BLO2] = 0;  st[SD_BHI] = st[SD_BHI2] = (uint32_t)count;
+    memcpy(r.hostSt, st, sizeof st);
+    MCU(m, cudaMemcpyAsync(s->counters, r.hostSt, sizeof st, cudaMemcpyHostToDevice, s->stream));
+    sph_system::Slab& b = s->slab;
+    const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+    sph_launch_slab_interior_hist(sph_launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->keyU, s->rankU, s->cellCount,
+                                  s->counters, r.capacity, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
+                                  (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 0);
+    enqueue_sort(r);
+    // the gather put the sorted velocities into velS (where a step's force kernel reads them); the live array is vel
+    MCU(m, cudaMemcpyAsync(s->vel, s->velS, (size_t)r.capacity * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+    MCU(m, cudaGetLastError());
+    MCU(m, cudaStreamSynchronize(s->stream));
+    s->stepped = false;
+    r.owned = count;
+    return SPH_OK;
+}
+
 int create_common(sph_multi* m, const SimParams* p, int capacity)
 {
     m->par = *p;
@@ -236,6 +264,7 @@ int create_common(sph_multi* m, const SimParams* p, int capacity)
         MCU(m, cudaStreamCreateWithFlags(&r.xs, cudaStreamNonBlocking));
         cudaEvent_t* evs[] = {&r.evA, &r.evX1, &r.evDp, &r.evX2};
         for (cudaEvent_t* e : evs) MCU(m, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t& e : r.evPhase) MCU(m, cudaEventCreate(&e));
         MCU(m, cudaMallocHost((void**)&r.hostSt, SD_WORDS * sizeof(uint32_t)));
         memset(r.hostSt, 0, SD_WORDS * sizeof(uint32_t));
     }
@@ -317,6 +346,7 @@ extern "C" int sph_multi_destroy(sph_multi_t* m)
         free_messages(r);
         cudaEvent_t evs[] = {r.evA, r.evX1, r.evDp, r.evX2};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : r.evPhase) if (e) cudaEventDestroy(e);
         if (r.xs) cudaStreamDestroy(r.xs);
         if (r.hostSt) cudaFreeHost(r.hostSt);
         if (r.s) sph_destroy(r.s);
@@ -449,25 +479,7 @@ extern "C" int sph_multi_set_state(sph_multi_t* m, const float* pos, const float
         // staged through the list buffer (192 bytes per slot, rebuilt by every step)
         float* stage = reinterpret_cast<float*>(s->nlist);
         MCU(m, cudaMemcpyAsync(stage, rec.data(), (size_t)mine * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-        if (sph_slab_set_owned(s, stage, (int)mine) != SPH_OK) return mfail(m, SPH_ERR_CUDA, "slab %d: %s", r.rank, sph_last_error(s));
-        // device words: the work set is the owned particles, nothing sorted yet; then one sort without integration
-        uint32_t st[SD_WORDS] = {};
-        st[SD_WORK] = st[SD_WORK0] = st[SD_END] = st[SD_G2] = (uint32_t)mine;
-        st[SD_BLO] = st[SD_BLO2] = 0;  st[SD_BHI] = st[SD_BHI2] = (uint32_t)mine;
-        memcpy(r.hostSt, st, sizeof st);
-        MCU(m, cudaMemcpyAsync(s->counters, r.hostSt, sizeof st, cudaMemcpyHostToDevice, s->stream));
-        sph_system::Slab& b = s->slab;
-        const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
-        sph_launch_slab_interior_hist(sph_launcher(s), s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->keyU, s->rankU, s->cellCount,
-                                      s->counters, r.capacity, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
-                                      (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 0);
-        enqueue_sort(r);
-        // the gather put the sorted velocities into velS (where a step's force kernel reads them); the live array is vel
-        MCU(m, cudaMemcpyAsync(s->vel, s->velS, (size_t)r.capacity * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        MCU(m, cudaGetLastError());
-        MCU(m, cudaStreamSynchronize(s->stream));
-        s->stepped = false;
-        r.owned = (int)mine;
+        if (int rc = load_slab(m, r, stage, (int)mine)) return rc;
     }
     m->haveState = true;
     return SPH_OK;
@@ -487,6 +499,8 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             MCU(m, cudaSetDevice(r.device));
             SphLaunch L = sph_launcher(s);
             const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+            auto mark = [&](int k) { if (m->phaseTiming) cudaEventRecord(r.evPhase[k], s->stream); };
+            mark(0);
             if (m->copyExchange && multi) {
                 // the neighbours pulled this slab's out buffers on THEIR exchange streams: wait for last step's pulls
                 if (r.hasLower) { MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX1, 0));  MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX2, 0)); }
@@ -504,9 +518,11 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
                                                         reinterpret_cast<uint32_t*>(r.msgDown), reinterpret_cast<uint32_t*>(r.msgUp));
                 MCU(m, cudaEventRecord(r.evA, s->stream));
             }
+            mark(1);
             sph_launch_slab_interior_hist(L, s->par, s->pos[s->cur], s->vel, s->idx[s->cur], s->keyU, s->rankU, s->cellCount,
                                           s->counters, r.capacity, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
                                           (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 1);
+            mark(2);
         }
         if (multi)
             if (int rc = exchange(m, msg_bytes(m), &MultiRank::evA, &MultiRank::msgDown, &MultiRank::msgUp, &MultiRank::inBelow, &MultiRank::inAbove)) return rc;
@@ -517,25 +533,31 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             MCU(m, cudaSetDevice(r.device));
             SphLaunch L = sph_launcher(s);
             const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
+            auto mark = [&](int k) { if (m->phaseTiming) cudaEventRecord(r.evPhase[k], s->stream); };
             if (multi) {
                 MCU(m, cudaEventRecord(r.evX1, r.xs));
                 MCU(m, cudaStreamWaitEvent(s->stream, r.evX1, 0));
+                mark(3);
                 sph_launch_slab_unpack_hist(L, s->par, r.hasLower ? r.inBelow : nullptr, r.hasUpper ? r.inAbove : nullptr,
                                             r.hasLower ? r.msgDown : nullptr, r.hasUpper ? r.msgUp : nullptr, capL, capB,
                                             s->pos[s->cur], s->vel, s->idx[s->cur], r.capacity, s->keyU, s->rankU, s->cellCount,
                                             s->counters, b.keyOffset, b.numCellsLocal, (uint32_t)(b.lowLayers * yx),
                                             (uint32_t)((b.lowLayers + nz) * yx), s->keyMax);
-            }
+            } else mark(3);
+            mark(4);
             enqueue_sort(r);
+            mark(5);
             const uint32_t* dev = s->counters + SD_FIRST;
             if (s->timing) cudaEventRecord(s->ev[3], s->stream);
             sph_launch_density(L, s->cfg, b.parLocal, s->pos[s->cur], s->velS, s->keyS, s->cellStart, s->maxCount, s->posP, s->velD,
                                s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, r.capacity, dev);
             if (s->timing) cudaEventRecord(s->ev[4], s->stream);
+            mark(6);
             if (multi) {
                 sph_launch_slab_pack_dp(L, s->posP, s->velD, s->counters, r.dpDown, r.dpUp, capB);
                 MCU(m, cudaEventRecord(r.evDp, s->stream));
             }
+            mark(7);
         }
         if (multi)
             if (int rc = exchange(m, dp_bytes(m), &MultiRank::evDp, &MultiRank::dpDown, &MultiRank::dpUp, &MultiRank::dpBelow, &MultiRank::dpAbove)) return rc;
@@ -546,19 +568,24 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             MCU(m, cudaSetDevice(r.device));
             SphLaunch L = sph_launcher(s);
             const uint32_t* dev = s->counters + SD_FIRST;
+            auto mark = [&](int k) { if (m->phaseTiming) cudaEventRecord(r.evPhase[k], s->stream); };
             if (s->timing) cudaEventRecord(s->evForce[0], s->stream);
             auto force = [&](int part) {
                 sph_launch_force(L, s->cfg, b.parLocal, s->posP, s->velD, s->velS, s->keyS, s->cellStart, s->maxCount, s->nlist, s->ncount,
-                                 s->ctaRows, s->vel, 0, r.capacity, 0, -1, dev, part);
+                                 s->ctaRows, s->vel, 0, r.capacity, 0, -1, dev, part, 2 * (capB / s->cfg.threads + 2));
             };
             if (multi) {
                 MCU(m, cudaEventRecord(r.evX2, r.xs));
                 force(1);
+                mark(8);
                 MCU(m, cudaStreamWaitEvent(s->stream, r.evX2, 0));
+                mark(9);
                 sph_launch_slab_unpack_dp(L, r.hasLower ? r.dpBelow : nullptr, r.hasUpper ? r.dpAbove : nullptr, s->counters, s->posP, s->velD, capB);
+                mark(10);
                 force(2);
-            } else force(0);
+            } else { force(0);  mark(8);  mark(9);  mark(10); }
             if (sph_needs_obstacles(s->par)) sph_launch_obstacles(L, b.parLocal, s->posP, s->velD, s->vel, 0, r.capacity, dev);
+            mark(11);
             if (s->timing) cudaEventRecord(s->evForce[1], s->stream);
             s->stepped = true;
             MCU(m, cudaGetLastError());
@@ -624,5 +651,60 @@ extern "C" int sph_multi_get_state(sph_multi_t* m, float* pos, float* vel, float
         total += count;
     }
     if (written) *written = total;
+    return SPH_OK;
+}
+
+// The owned particles of one local slab as 48-byte records {pos xyzw, vel xyzw, (original index, rho, p, 0)} to / from HOST
+// memory (pinned memory makes the copies asynchronous until the final wait).  put: the records must lie in the slab's layers
+// (what a fetch returned, possibly modified); the slab is re-sorted and ready to step.
+extern "C" int sph_multi_fetch_owned(sph_multi_t* m, int local, float* hostRecords, int capacityRecords, int* count)
+{
+    if (!m || local < 0 || local >= (int)m->ranks.size() || !hostRecords || !count) return SPH_ERR_ARG;
+    MultiRank& r = m->ranks[local];
+    if (int rc = sync_rank(m, r)) return rc;
+    sph_system* s = r.s;
+    const int first = (int)r.hostSt[SD_FIRST], n = (int)(r.hostSt[SD_END] - r.hostSt[SD_FIRST]);
+    *count = n;
+    if (n > capacityRecords) return mfail(m, SPH_ERR_ARG, "sph_multi_fetch_owned: %d records, room for %d", n, capacityRecords);
+    if (n <= 0) return SPH_OK;
+    float* stage = reinterpret_cast<float*>(s->nlist);
+    sph_launch_slab_export(sph_launcher(s), s->pos[s->cur], s->vel, s->idx[s->cur], s->stepped ? s->posP : nullptr,
+                           s->stepped ? s->velD : nullptr, first, n, stage);
+    MCU(m, cudaMemcpyAsync(hostRecords, stage, (size_t)n * kRecFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    MCU(m, cudaStreamSynchronize(s->stream));
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_put_owned(sph_multi_t* m, int local, const float* hostRecords, int count)
+{
+    if (!m || local < 0 || local >= (int)m->ranks.size() || !hostRecords || count < 0) return SPH_ERR_ARG;
+    if (!m->haveState) return mfail(m, SPH_ERR_STATE, "sph_multi_put_owned: call sph_multi_set_state first (it fixes the cuts)");
+    MultiRank& r = m->ranks[local];
+    if (count > r.capacity) return mfail(m, SPH_ERR_ARG, "sph_multi_put_owned: %d records exceed the slab capacity %d", count, r.capacity);
+    sph_system* s = r.s;
+    MCU(m, cudaSetDevice(r.device));
+    MCU(m, cudaStreamSynchronize(r.xs));
+    float* stage = reinterpret_cast<float*>(s->nlist);
+    MCU(m, cudaMemcpyAsync(stage, hostRecords, (size_t)count * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    return load_slab(m, r, stage, count);
+}
+
+// Phase profile of the LAST step of one local slab, milliseconds on its solver stream (enable first; costs a dozen event
+// records per step).  out11 = {edge integrate + pack, interior integrate + histogram, wait for the particle exchange,
+// unpack + histogram of arrivals, scan + bucket + gather, density, pack rho/p rows, interior force, wait for the rho/p
+// exchange, unpack rho/p rows, boundary force}.
+extern "C" int sph_multi_phase_ms(sph_multi_t* m, int local, int enable, float* out11)
+{
+    if (!m || local < 0 || local >= (int)m->ranks.size()) return SPH_ERR_ARG;
+    MultiRank& r = m->ranks[local];
+    if (out11) {
+        if (int rc = sync_rank(m, r)) return rc;
+        for (int k = 0; k < 11; k++) {
+            float ms = -1.f;
+            if (!m->phaseTiming || m->steps == 0 || cudaEventElapsedTime(&ms, r.evPhase[k], r.evPhase[k + 1]) != cudaSuccess) { ms = -1.f;  cudaGetLastError(); }
+            out11[k] = ms;
+        }
+    }
+    m->phaseTiming = enable != 0;
     return SPH_OK;
 }

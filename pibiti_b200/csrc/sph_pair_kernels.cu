@@ -604,6 +604,15 @@ __device__ __forceinline__ bool pair_cta_in_part(int p0, int perCta, int n, cons
     return part == 1 ? interior : !interior;
 }
 
+// part 2 is launched over a COMPACT grid (the two boundary layers are a small fraction of the slab): block b is the b-th
+// CTA that touches the first owned layer, or, past those, the CTAs from the one that reaches into the last owned layer on.
+__device__ __forceinline__ int pair_part2_cta(int block, int first, int perCta, const uint32_t* __restrict__ dev)
+{
+    const int nLo = ((int)__ldg(dev + 2) - first + perCta - 1) / perCta;
+    const int hiStart = max(nLo, ((int)__ldg(dev + 3) - first) / perCta);
+    return block < nLo ? block : hiStart + (block - nLo);
+}
+
 // ---- L1-cached variant ------------------------------------------------------------------------------
 // Same walk and same arithmetic, but candidates are read straight from the sorted arrays through L1
 // (LDG.128 on the read-only path) instead of being staged by TMA: no shared memory, no CTA prologue,
@@ -725,9 +734,10 @@ k_force_l1(const __grid_constant__ SimParams par, int kMax,
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
-    const int cta = blockIdx.x + ctaFirst;     // a launch may cover a sub-range of the CTAs the density launch used
+    int cta = blockIdx.x + ctaFirst;           // a launch may cover a sub-range of the CTAs the density launch used
     if (dev) {
         first = (int)__ldg(dev);  n = (int)__ldg(dev + 1);
+        if (part == 2) cta = pair_part2_cta(blockIdx.x, first, T, dev);
         if (!pair_cta_in_part(first + cta * T, T, n, dev, part)) return;
     }
     const int i = first + cta * T + threadIdx.x;
@@ -951,9 +961,10 @@ k_force_rm(const __grid_constant__ SimParams par, int recCap,
 {
     __shared__ StageTable st;                  // only read by the (never staged) filtering walk
     const int T = blockDim.x;
-    const int cta = blockIdx.x + ctaFirst;     // a launch may cover a sub-range of the CTAs the density launch used
+    int cta = blockIdx.x + ctaFirst;           // a launch may cover a sub-range of the CTAs the density launch used
     if (dev) {
         first = (int)__ldg(dev);  n = (int)__ldg(dev + 1);
+        if (part == 2) cta = pair_part2_cta(blockIdx.x, first, T, dev);
         if (!pair_cta_in_part(first + cta * T, T, n, dev, part)) return;
     }
     const int i = first + cta * T + threadIdx.x;
@@ -1066,11 +1077,12 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
                       const float4* posP, const float4* velD, const float4* velS, const uint32_t* keyS,
                       const uint32_t* cellStart, const uint32_t* maxCount, const void* nlist, const uint16_t* ncount,
                       const uint32_t* ctaRows, float4* velOut, int first, int count, int ctaFirst, int ctaCount,
-                      const uint32_t* dev, int part)
+                      const uint32_t* dev, int part, int part2Blocks)
 {
     if (count <= 0) return;
     const int n = first + count;
     int blocks = (int)sph_pair_blocks(cfg, count);
+    if (dev && part == 2 && part2Blocks > 0 && part2Blocks < blocks) blocks = part2Blocks;     // compact grid, see pair_part2_cta
     if (cfg.mode != SPH_PAIR_TMA && ctaCount >= 0) {            // sub-range of the CTAs (slab mode: interior / boundary)
         if (ctaFirst < 0 || ctaFirst + ctaCount > blocks) ctaCount = blocks - ctaFirst;
         if (ctaCount <= 0) return;

@@ -770,6 +770,7 @@ k_slab_interior_hist(const __grid_constant__ SimParams par, const BoundaryCtx ct
     const uint32_t work = st[SD_END];
     if (i == 0) { st[SD_WORK0] = work;  st[SD_WORK] = work; }       // the unpack kernel appends behind this
     uint32_t live1 = 0;
+    bool isDummy = false;
     if (i < work) {
         const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO2], bHi = st[SD_BHI2];
         const bool owned = i >= g0 && i < g1;
@@ -790,8 +791,13 @@ k_slab_interior_hist(const __grid_constant__ SimParams par, const BoundaryCtx ct
             if (key != (uint32_t)numCellsLocal) live1 = key + 1;
         }
         keyU[i] = key;
-        rankU[i] = atomicAdd(&cellCount[key], 1u);
+        isDummy = key == (uint32_t)numCellsLocal;
+        if (!isDummy) rankU[i] = atomicAdd(&cellCount[key], 1u);
     }
+    // retired slots (last step's ghosts, leavers) all count into the ONE dummy cell: one atomic per warp, not per slot --
+    // same-address atomics serialise in L2, and there is a boundary layer's worth of them every step
+    const uint32_t slot = warp_append_slot(&cellCount[numCellsLocal], isDummy);
+    if (isDummy) rankU[i] = slot;
     live1 = __reduce_max_sync(0xffffffffu, live1);
     if ((threadIdx.x & 31) == 0 && live1) atomicMax(&blockMax, live1);
     __syncthreads();

@@ -87,7 +87,8 @@ ABI_SYMBOLS = (
     "sph_slab_unpack_dp", "sph_slab_force", "sph_slab_force_part", "sph_slab_stats",
     "sph_multi_unique_id", "sph_multi_create", "sph_multi_create_rank", "sph_multi_destroy", "sph_multi_last_error",
     "sph_multi_set_params", "sph_multi_set_state", "sph_multi_step", "sph_multi_sync", "sph_multi_get_state",
-    "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info",
+    "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info", "sph_multi_fetch_owned", "sph_multi_put_owned",
+    "sph_multi_phase_ms",
 )
 
 
@@ -161,6 +162,9 @@ def load() -> C.CDLL:
     lib.sph_multi_step.argtypes = [vp, ci]
     lib.sph_multi_sync.argtypes = [vp]
     lib.sph_multi_get_state.argtypes = [vp, vp, vp, vp, vp, ci, ip]
+    lib.sph_multi_fetch_owned.argtypes = [vp, ci, vp, ci, ip]
+    lib.sph_multi_put_owned.argtypes = [vp, ci, vp, ci]
+    lib.sph_multi_phase_ms.argtypes = [vp, ci, ci, vp]
     lib.sph_multi_local_slabs.argtypes = [vp]
     lib.sph_multi_handle.argtypes = [vp, ci]
     lib.sph_multi_handle.restype = vp
@@ -359,6 +363,26 @@ class MultiSystem:
         self._check(self.lib.sph_multi_get_state(self.h, _ptr(pos), _ptr(vel), _ptr(dens) if density else None,
                                                  _ptr(pres) if density else None, n, C.byref(w)), "sph_multi_get_state")
         return (pos, vel, dens, pres, w.value) if density else (pos, vel, w.value)
+
+    def fetch_owned(self, local: int, host_ptr: int, capacity_records: int) -> int:
+        """Owned records of a local slab into host memory at `host_ptr` (e.g. a pinned torch tensor); returns the count."""
+        c = C.c_int(0)
+        self._check(self.lib.sph_multi_fetch_owned(self.h, local, C.c_void_p(host_ptr), capacity_records, C.byref(c)), "sph_multi_fetch_owned")
+        return c.value
+
+    def put_owned(self, local: int, host_ptr: int, count: int):
+        self._check(self.lib.sph_multi_put_owned(self.h, local, C.c_void_p(host_ptr), count), "sph_multi_put_owned")
+
+    PHASES = ("edge_integrate_pack", "interior_integrate_hist", "wait_particle_exchange", "unpack_arrivals", "scan_bucket_gather",
+              "density", "pack_rho_p", "interior_force", "wait_rho_p_exchange", "unpack_rho_p", "boundary_force")
+
+    def enable_phase_timing(self, on: bool = True):
+        self._check(self.lib.sph_multi_phase_ms(self.h, 0, int(on), None), "sph_multi_phase_ms")
+
+    def phase_ms(self, local: int = 0) -> dict:
+        out = np.zeros(11, np.float32)
+        self._check(self.lib.sph_multi_phase_ms(self.h, local, 1, _ptr(out)), "sph_multi_phase_ms")
+        return dict(zip(self.PHASES, [round(float(x), 4) for x in out]))
 
     def local_slabs(self) -> int:
         return int(self.lib.sph_multi_local_slabs(self.h))

@@ -18,8 +18,11 @@ Every exchange is a pair of nearest-neighbour send/recv (torch.distributed batch
 NVLink, ordered on the solver's CUDA stream; gloo for the CPU tests).  No collective sits on the data path and
 the host synchronises once per step (the read-back after the sort).
 
+This module is the PROTOCOL MODEL of the decomposition, kept for the tests: the production driver is C++
+(pibiti_b200/csrc/sph_multi.cu, `sph_multi_*` in include/sph_b200.h, `lib.MultiSystem`), which runs the same phases
+with device-resident bookkeeping, its own NCCL communicator and no host synchronisation; bench.py uses that one.
 `slab_step` is written over a list of ranks plus a communicator so that the same code drives
-  * one rank per process with `DistComm` (production, bench.py under torchrun), and
+  * one rank per process with `DistComm` (gloo on the CPU with the oracle backend; NCCL also works), and
   * all ranks inside one process with `LocalComm` (tests on a single GPU / on the CPU).
 The per-rank work is delegated to a backend object; `GpuSlabBackend` wraps one sph_t handle in slab mode.
 """
@@ -411,136 +414,4 @@ def gather_by_id(record_arrays, n):
     assert rec.shape[0] == n and np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "particles lost or duplicated"
     out = np.empty_like(rec)
     out[ids] = rec
-    return out
-
-
-# -------------------------------------------------------------------------------------------------
-def bench_multi(args, metric, unit, stage_bytes, peaks, ClockSampler):
-    """bench.py under torchrun: weak scaling, 8M particles per GPU, z-slab-decomposed wave tank."""
-    import torch
-    import torch.distributed as dist
-    from . import host
-
-    # `bench.py --slab` without torchrun: a one-rank job still needs the env:// rendezvous variables
-    for k, v in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0"), ("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29533")):
-        os.environ.setdefault(k, v)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dist.barrier()
-    title = args.workload or {1: "wave tank 8M", 2: "wave tank 16M", 4: "wave tank 32M", 8: "wave tank 64M"}[world]
-
-    s = host.CSph(device=-1)                     # scene + initial lattice on the host (every rank builds the same one)
-    s.select_scene(title)
-    par = s.params
-    pos, vel = s.host_arrays()
-    n = s.n
-    cuts, parts = split_initial_state(par, pos, vel, world)
-    mine = parts[rank]
-    caps = SlabCaps.for_state(par, pos, cuts)
-    capacity = int(mine.shape[0] * 1.25) + 4 * caps.rows
-    be = GpuSlabBackend(par, capacity, cuts[rank], cuts[rank + 1], rank > 0, rank < world - 1, local, caps)
-    be.set_owned(mine)
-    del pos, vel, parts
-    comm = DistComm(rank, world)
-    stream = be.stream
-
-    prof = {} if os.environ.get("SPH_SLAB_PROFILE") else None
-    be.sys.enable_timings(True)                  # event records around the pair kernels: no synchronisation
-
-    def one_step():
-        s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
-        be.set_params(s.params)
-        slab_step([be], comm, prof)
-
-    warm = max(args.warmup, 3)
-    for _ in range(warm):
-        one_step()
-    if prof is not None:
-        prof.clear()                             # NCCL connection set-up happened in the first exchange
-    be.sync()
-    dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = be.sys.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        one_step()
-    e1.record(stream)
-    be.sync()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.barrier()
-    wall = time.perf_counter() - t0
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = be.sys.launch_count() - l0
-    kernel_ms = {k: v for k, v in be.sys.timings().items() if v >= 0}      # last timed step, this rank
-    owned_timed = be.n_owned
-    clocks = sampler.stop() if rank == 0 else None
-    owned = torch.tensor([be.n_owned], device="cuda", dtype=torch.int64)
-    counts = [torch.zeros_like(owned) for _ in range(world)]
-    dist.all_gather(counts, owned)
-    ms_total = float(ms.item())
-
-    # end to end with HOST buffers: every step uploads the rank's owned records from pinned memory and reads them back
-    e2e_steps = max(3, min(args.steps, 5))
-    host_rec = torch.empty((be.n_owned, REC), dtype=torch.float32, pin_memory=True)
-    host_rec.copy_(be.get_owned())
-    dist.barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(e2e_steps):
-        dev = host_rec.to(be.device, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        be.set_owned(dev)
-        h2d += dev.numel() * 4
-        one_step()
-        out = be.get_owned()
-        host_rec = torch.empty((out.shape[0], REC), dtype=torch.float32, pin_memory=True)
-        host_rec.copy_(out)
-        d2h += out.numel() * 4
-    be.sync()
-    dist.barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    io = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
-    dist.all_reduce(io)
-
-    hbm, hbm_src = peaks
-    out = {
-        "metric": metric, "value": n * args.steps / (ms_total * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": title, "particles": n, "particles_per_gpu": [int(c.item()) for c in counts],
-                   "slab_cuts_z_layers": cuts, "grid": [int(x) for x in par["gridSize"][0]], "scene_file": "scenes/Scenes.xml",
-                   "parallelism": f"z-slab x{world}, 1-layer halo, NCCL send/recv",
-                   "l2": "per-GPU state is far larger than L2; no flush needed",
-                   "timing": "CUDA events on the solver stream, max over ranks", "wall_s": round(wall, 3)},
-        "clocks": clocks,
-        "e2e": {"value": n * e2e_steps / float(e2e_s.item()), "unit": unit,
-                "h2d_bytes_per_step": int(io[0].item()) // e2e_steps, "d2h_bytes_per_step": int(io[1].item()) // e2e_steps,
-                "steps": e2e_steps, "api": "per rank: owned records pinned host -> device, slab step, device -> pinned host"},
-        "gpu_launches": int(launches),
-        "halo_bytes_per_step_rank0": comm.bytes_sent // max(args.steps + warm + e2e_steps, 1),
-        "phase_ms_by_rank": _gather_profile(dist, prof, args.steps + e2e_steps, world,
-                                             {"kernel_ms_last_step": {k: round(v, 3) for k, v in be.sys.timings().items() if v >= 0},
-                                              "stats": be.stats()})
-        if prof is not None else None,
-        "roofline": None,
-    }
-    dom = max((k for k in ("density", "force") if k in kernel_ms), key=lambda k: kernel_ms[k], default=None)
-    if dom is not None and kernel_ms[dom] > 0:
-        achieved = stage_bytes[dom] * owned_timed / (kernel_ms[dom] * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": {"density": "k_density_rm", "force": "k_force_rm"}[dom],
-                           "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
-                           "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_particle": stage_bytes[dom],
-                           "note": "rank 0, last timed step, owned particles only; the single-GPU line carries the ncu traffic",
-                           "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()}}
     return out

@@ -26,7 +26,7 @@ def main():
     s = host.CSph(device=-1)
     s.select_scene(title)
     pos, vel = s.host_arrays()
-    m = lib.MultiSystem(s.params, capacity_per_slab=int(s.n / world * 1.6) + 40000, rank=rank, world=world, unique_id=ids[0], device=local)
+    m = lib.MultiSystem(s.params, capacity_per_slab=s.n, rank=rank, world=world, unique_id=ids[0], device=local)
     m.set_state(pos, stir(vel))
     for _ in range(steps):
         s.UpdateEmitter()
