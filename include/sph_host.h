@@ -107,6 +107,10 @@ public:
     // device >= 0: allocate the solver on that GPU.  device < 0: scene/initialiser layer only
     // (no GPU touched; Update() fails) -- used to load and inspect Scenes.xml.
     explicit cSPH(const char* scenesXmlPath = "Scenes.xml", int device = 0);
+    // Several GPUs of one box: the system is cut into z slabs, one per device, and stepped by the multi-GPU driver
+    // (sph_multi_*, sph_b200.h) -- same Update / getArray / setArray / scene interface, results bit-identical to one GPU.
+    // Not available in this mode: GL interop, the dye / colour outputs, scenes with a Z wrap/cycle or pump boundary.
+    cSPH(const char* scenesXmlPath, const int* devices, int ndev);
     ~cSPH();
 
     void _InitMem(), _FreeMem();
@@ -144,6 +148,7 @@ public:
     int LoadState(const char* path);
 
     sph_t* solver() const { return sys; }
+    sph_multi_t* multiSolver() const { return msys; }         // non-null when constructed with a device list
     const char* lastError() const { return err.c_str(); }
 
     float4 *hPos, *hVel;                        // host mirrors, original particle order
@@ -157,6 +162,11 @@ private:
     std::string xmlPath;
     int device;
     sph_t* sys;
+    std::vector<int> devices;                   // multi-GPU mode: the device list (empty otherwise)
+    sph_multi_t* msys;
+    bool multiDirty;                            // multi-GPU mode: the host mirrors hold changes the slabs have not seen yet
+    int multiSync();                            // ... bring the mirrors up to date with the slabs (before a partial write)
+    int multiFlush();                           // ... push the mirrors to the slabs (before a step)
     std::string err;
     size_t memParticles, memCells;              // what the device buffers of `sys` were allocated for
 };

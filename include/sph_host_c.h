@@ -23,6 +23,9 @@ typedef struct sphh_system sphh_t;
 
 /* device >= 0: solver on that GPU; device < 0: scene / initialiser layer only (no GPU touched) */
 sphh_t* sphh_create(const char* scenesXmlPath, int device);
+/* several GPUs of one box (z slabs, multi-GPU driver of sph_b200.h); same interface, results identical to one GPU */
+sphh_t* sphh_create_multi(const char* scenesXmlPath, const int* devices, int ndev);
+sph_multi_t* sphh_multi_solver(sphh_t* h);                         /* NULL unless created with a device list */
 void sphh_destroy(sphh_t* h);
 const char* sphh_last_error(sphh_t* h);
 

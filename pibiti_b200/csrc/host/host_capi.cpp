@@ -14,10 +14,16 @@ sphh_t* sphh_create(const char* scenesXmlPath, int device)
     return reinterpret_cast<sphh_t*>(new cSPH(scenesXmlPath, device));
 }
 
+sphh_t* sphh_create_multi(const char* scenesXmlPath, const int* devices, int ndev)
+{
+    return reinterpret_cast<sphh_t*>(new cSPH(scenesXmlPath, devices, ndev));
+}
+
 void sphh_destroy(sphh_t* h) { delete reinterpret_cast<cSPH*>(h); }
 
 static cSPH* S(sphh_t* h) { return reinterpret_cast<cSPH*>(h); }
 
+sph_multi_t* sphh_multi_solver(sphh_t* h) { return S(h)->multiSolver(); }
 int sphh_num_scenes(sphh_t* h) { return (int)S(h)->scenes.size(); }
 int sphh_cur_scene(sphh_t* h) { return S(h)->curScene; }
 const char* sphh_last_error(sphh_t* h) { return S(h)->lastError(); }

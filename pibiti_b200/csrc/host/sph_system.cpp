@@ -60,7 +60,17 @@ bool Timer::update(bool updFR)
 cSPH::cSPH(const char* scenesXmlPath, int dev)
     : bInitialized(false), curScene(0), hPos(nullptr), hVel(nullptr), hCounters(nullptr), colorVbo(0),
       curPosRead(0), curPosWrite(1), xmlPath(scenesXmlPath ? scenesXmlPath : "Scenes.xml"), device(dev), sys(nullptr),
-      memParticles(0), memCells(0)
+      msys(nullptr), multiDirty(false), memParticles(0), memCells(0)
+{
+    posVbo[0] = posVbo[1] = 0;
+    DropPos = f3(0, 0, 0);
+    LoadScenes();
+}
+
+cSPH::cSPH(const char* scenesXmlPath, const int* devs, int ndev)
+    : bInitialized(false), curScene(0), hPos(nullptr), hVel(nullptr), hCounters(nullptr), colorVbo(0),
+      curPosRead(0), curPosWrite(1), xmlPath(scenesXmlPath ? scenesXmlPath : "Scenes.xml"), device(ndev > 0 ? devs[0] : -1), sys(nullptr),
+      devices(devs, devs + (ndev > 0 ? ndev : 0)), msys(nullptr), multiDirty(false), memParticles(0), memCells(0)
 {
     posVbo[0] = posVbo[1] = 0;
     DropPos = f3(0, 0, 0);
@@ -71,6 +81,26 @@ cSPH::~cSPH()
 {
     _FreeMem();
     if (sys) { sph_destroy(sys);  sys = nullptr; }
+    if (msys) { sph_multi_destroy(msys);  msys = nullptr; }
+}
+
+// ---- multi-GPU mode: the slabs are authoritative after a step, the host mirrors after a write -----
+
+int cSPH::multiSync()
+{
+    if (!msys || multiDirty) return SPH_OK;                 // the mirrors already hold the newest state
+    int rc = sph_multi_get_state(msys, (float*)hPos, (float*)hVel, nullptr, nullptr, (int)scn.params.numParticles, nullptr);
+    if (rc != SPH_OK) err = sph_multi_last_error(msys);
+    return rc;
+}
+
+int cSPH::multiFlush()
+{
+    if (!msys || !multiDirty) return SPH_OK;
+    int rc = sph_multi_set_params(msys, &scn.params);
+    if (rc == SPH_OK) rc = sph_multi_set_state(msys, (const float*)hPos, (const float*)hVel, (int)scn.params.numParticles, nullptr);
+    if (rc != SPH_OK) err = sph_multi_last_error(msys); else multiDirty = false;
+    return rc;
 }
 
 // ---- memory ------------------------------------------------------------------------------------
@@ -84,6 +114,15 @@ void cSPH::_InitMem()
     hVel = new float4[npar];  memset(hVel, 0, npar * sizeof(float4));
     hCounters = new int[10];  memset(hCounters, 0, 10 * sizeof(int));     // SPH_Mem.cpp:24
     if (device < 0) return;
+    if (devices.size() > 1) {
+        // one slab per device; a slab holds its share of the particles plus ghosts, arrivals and drift of the balance
+        if (msys) { sph_multi_destroy(msys);  msys = nullptr; }
+        const size_t cap = npar / devices.size() * 3 / 2 + 65536;
+        int rc = sph_multi_create(&scn.params, (int)devices.size(), devices.data(), (int)(cap < npar + 4096 ? cap : npar + 4096), &msys);
+        if (rc != SPH_OK) { err = sph_multi_last_error(nullptr);  msys = nullptr;  fprintf(stderr, "cSPH: %s\n", err.c_str()); }
+        multiDirty = true;                                  // the first Update pushes whatever Reset / setArray put in the mirrors
+        return;
+    }
     // A scene that fits the device buffers of the previous one keeps them (the reference frees and reallocates
     // everything on every scene switch, SPH_Scenes.cpp:9-13 -> SPH_Mem.cpp:11-82): only the parameters change.
     if (sys && npar <= memParticles && scn.params.numCells <= memCells) {
@@ -241,6 +280,17 @@ int cSPH::Update() { return Update(1); }
 int cSPH::Update(int nsteps)
 {
     if (!bInitialized) return SPH_ERR_STATE;
+    if (msys) {
+        tim.update(true);
+        if (int rc = multiFlush()) return rc;
+        if (app.bChangedAny) {
+            app.bChangedAny = false;
+            if (sph_multi_set_params(msys, &scn.params) != SPH_OK) { err = sph_multi_last_error(msys);  return SPH_ERR_PARAMS; }
+        }
+        int rc = sph_multi_step(msys, nsteps);
+        if (rc != SPH_OK) err = sph_multi_last_error(msys);
+        return rc;
+    }
     if (!sys) { if (err.empty()) err = "cSPH::Update: no solver (constructed without a device)";  return SPH_ERR_STATE; }
     tim.update(true);                                       // SPH_Update.cpp:16
     if (app.bChangedAny) {                                  // SPH_Update.cpp:19-27
@@ -256,6 +306,7 @@ int cSPH::Update(int nsteps)
 
 int cSPH::registerGLBuffers(uint positionsVbo, uint colorsVbo)
 {
+    if (msys) { err = "registerGLBuffers: not available with several GPUs (positions live in per-device slabs)";  return SPH_ERR_STATE; }
     if (!sys) { err = "registerGLBuffers: no solver";  return SPH_ERR_STATE; }
     int rc = sph_gl_register(sys, SPH_POS, positionsVbo);
     if (rc == SPH_OK) { posVbo[0] = posVbo[1] = positionsVbo; }
@@ -378,6 +429,7 @@ float4* cSPH::getArray(bool pos)
 {
     if (!bInitialized) return nullptr;
     float4* hdata = !pos ? hPos : hVel;                     // SPH_Util.cpp:48-52: false -> positions
+    if (msys) { multiSync();  return hdata; }
     if (sys) {
         int rc = sph_get_array(sys, !pos ? SPH_POS : SPH_VEL, (float*)hdata, 0, (int)scn.params.numParticles);
         if (rc != SPH_OK) err = sph_last_error(sys);
@@ -388,6 +440,19 @@ float4* cSPH::getArray(bool pos)
 void cSPH::setArray(bool pos, const float4* data, int start, int count)
 {
     if (!bInitialized || count <= 0) return;
+    if (msys) {
+        // a partial write needs the rest of the mirrors current first; the slabs see the result at the next Update
+        if (!(start == 0 && count == (int)scn.params.numParticles)) multiSync();
+        float4* mirror = !pos ? hPos : hVel;
+        if (data != mirror + start) memcpy(mirror + start, data, (size_t)count * sizeof(float4));
+        if (start == 0 && count == (int)scn.params.numParticles && !multiDirty) {
+            // the other array must be current as well before both are pushed
+            float4* keep = !pos ? hVel : hPos;
+            sph_multi_get_state(msys, !pos ? nullptr : (float*)keep, !pos ? (float*)keep : nullptr, nullptr, nullptr, count, nullptr);
+        }
+        multiDirty = true;
+        return;
+    }
     if (sys) {
         int rc = sph_set_array(sys, !pos ? SPH_POS : SPH_VEL, (const float*)data, start, count);
         if (rc != SPH_OK) err = sph_last_error(sys);

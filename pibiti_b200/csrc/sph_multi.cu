@@ -461,9 +461,10 @@ extern "C" int sph_multi_set_state(sph_multi_t* m, const float* pos, const float
         if (resize || !r.msgDown) if (int rc = alloc_messages(m, r)) return rc;
         long long mine = 0;
         for (int z = r.zLo; z < r.zHi; z++) mine += hist[z];
-        if (mine + 2LL * capB + 2LL * capL > r.capacity)
-            return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: slab %d owns %lld particles; with ghosts and arrivals that exceeds its "
-                         "capacity of %d slots", r.rank, mine, r.capacity);
+        // a step's work set: last step's ghosts below + owned + arrivals + new ghosts on both sides (+ own leavers)
+        if (mine + 4LL * fullest + 1024 > r.capacity)
+            return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: slab %d owns %lld particles; with ghosts and arrivals (layers of up to "
+                         "%lld) that exceeds its capacity of %d slots", r.rank, mine, fullest, r.capacity);
         rec.resize((size_t)std::max<long long>(mine, 1) * kRecFloats);
         size_t k = 0;
         for (int i = 0; i < n; i++) {

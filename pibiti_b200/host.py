@@ -24,7 +24,7 @@ HOST_ABI_SYMBOLS = (
     "sphh_reset", "sphh_drop", "sphh_emit_id", "sphh_srand", "sphh_update_emitter", "sphh_update",
     "sphh_mark_changed", "sphh_get_array", "sphh_set_array", "sphh_solver", "sphh_load_options",
     "sphh_save_state", "sphh_load_state", "sphh_set_targets", "sphh_set_emitter", "sphh_cnt_rain", "sphh_changed_flag",
-    "sphh_register_gl", "sphh_pos_buffer", "sphh_timer_fps",
+    "sphh_register_gl", "sphh_pos_buffer", "sphh_timer_fps", "sphh_create_multi", "sphh_multi_solver",
 )
 
 EXTRA_FIELDS = ("initMin", "initMax", "initType", "initLast", "spacing", "fCellSize", "dropR", "rain", "rVel", "r2Vel",
@@ -40,6 +40,8 @@ def _bind():
         return L
     vp, ci, cs = C.c_void_p, C.c_int, C.c_char_p
     L.sphh_create.restype = vp;            L.sphh_create.argtypes = [cs, ci]
+    L.sphh_create_multi.restype = vp;      L.sphh_create_multi.argtypes = [cs, C.POINTER(ci), ci]
+    L.sphh_multi_solver.restype = vp;      L.sphh_multi_solver.argtypes = [vp]
     L.sphh_destroy.argtypes = [vp]
     L.sphh_last_error.restype = cs;        L.sphh_last_error.argtypes = [vp]
     L.sphh_num_scenes.argtypes = [vp];     L.sphh_cur_scene.argtypes = [vp]
@@ -98,18 +100,28 @@ class _SolverView(_lib.SphSystem):
 class CSph:
     """The reference's `cSPH`, headless.  device < 0: scene layer only (no GPU is touched)."""
 
-    def __init__(self, scenes_xml: str | Path = DEFAULT_SCENES_XML, device: int = 0, seed: int | None = 1):
+    def __init__(self, scenes_xml: str | Path = DEFAULT_SCENES_XML, device: int = 0, seed: int | None = 1, devices=None):
+        """devices: a list of GPUs -> the system is cut into z slabs, one per device (cSPH's device-list constructor)."""
         self.L = _bind()
         if seed is not None:
             self.L.sphh_srand(seed)          # the reference never seeds rand(): glibc's default seed is 1
-        self.h = C.c_void_p(self.L.sphh_create(str(scenes_xml).encode(), device))
+        self.devices = list(devices) if devices is not None and len(devices) > 1 else None
+        if self.devices:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            self.h = C.c_void_p(self.L.sphh_create_multi(str(scenes_xml).encode(), arr, len(self.devices)))
+            device = self.devices[0]
+        else:
+            self.h = C.c_void_p(self.L.sphh_create(str(scenes_xml).encode(), device))
         if not self.h:
             raise SphError("sphh_create failed")
         self.device = device
         self._check_solver()
 
     def _check_solver(self):
-        if self.device >= 0 and not self.L.sphh_solver(self.h):
+        if self.devices:
+            if not self.L.sphh_multi_solver(self.h):
+                raise SphError("no multi-GPU solver: " + self.last_error())
+        elif self.device >= 0 and not self.L.sphh_solver(self.h):
             raise SphError("no solver: " + self.last_error())
 
     def close(self):

@@ -125,3 +125,25 @@ def test_multi_driver_nccl_two_processes(tmp_path):
     got = np.load(out)
     ref = single_gpu_run("wave tank 256k", steps)
     assert np.array_equal(got["pos"], ref[0]) and np.array_equal(got["vel"], ref[1]) and np.array_equal(got["dens"], ref[2])
+
+
+def test_csph_with_a_device_list_equals_one_device():
+    """cSPH(device list): Reset through the mirrors, a full-range setArray, steps, a PARTIAL setArray mid-run (what an
+    emitter does) and getArray -- identical to the one-device cSPH."""
+    def run(devices):
+        s = host.CSph(device=0, devices=devices)
+        s.select_scene("mini waves")
+        _, vel = s.host_arrays()
+        s.setArray(True, stir(vel))
+        for k in range(8):
+            s.UpdateEmitter()
+            s.Update()
+            if k == 3:
+                v = s.getArray(True)[100:228].copy()
+                v[:, 1] += 0.25
+                s.setArray(True, v, start=100)
+        out = s.getArray(False).copy(), s.getArray(True).copy()
+        s.close()
+        return out
+    one, three = run(None), run([0, 0, 0])
+    assert np.array_equal(one[0], three[0]) and np.array_equal(one[1], three[1])
