@@ -210,6 +210,12 @@ int sph_multi_put_owned(sph_multi_t* m, int local, const float* hostRecords, int
  * histogram, wait for the particle exchange, unpack arrivals, scan + bucket + gather, density, pack rho/p rows, interior
  * force, wait for the rho/p exchange, unpack rho/p rows, boundary force}; enable it first */
 int sph_multi_phase_ms(sph_multi_t* m, int local, int enable, float* out11);
+/* Re-cut the slabs from the layer histogram of the CURRENT state (the cuts of set_state balance the particle counts at
+ * t = 0 only): the slabs synchronise, particles move to their new owners, every slab re-sorts.  Results do not depend on
+ * the cuts.  sph_multi_set_recut_interval(m, M) makes sph_multi_step do it every M steps (0 = never). */
+int sph_multi_recut(sph_multi_t* m);
+int sph_multi_set_recut_interval(sph_multi_t* m, int steps);
+int sph_multi_recut_count(sph_multi_t* m);
 int sph_multi_local_slabs(sph_multi_t* m);
 sph_t* sph_multi_handle(sph_multi_t* m, int local);                             /* timings, dumps, launch counts of one slab */
 void* sph_multi_stream(sph_multi_t* m, int local);                              /* cudaStream_t the slab's kernels run on */

@@ -39,6 +39,8 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
 };
@@ -65,7 +67,7 @@ bool load_nccl(std::string& why)
     SYM(GetUniqueId, "ncclGetUniqueId")  SYM(CommInitRank, "ncclCommInitRank")  SYM(CommInitAll, "ncclCommInitAll")
     SYM(CommDestroy, "ncclCommDestroy")  SYM(GroupStart, "ncclGroupStart")      SYM(GroupEnd, "ncclGroupEnd")
     SYM(Send, "ncclSend")                SYM(Recv, "ncclRecv")                  SYM(GetErrorString, "ncclGetErrorString")
-    SYM(GetVersion, "ncclGetVersion")
+    SYM(GetVersion, "ncclGetVersion")   SYM(AllReduce, "ncclAllReduce")        SYM(AllGather, "ncclAllGather")
 #undef SYM
     g_nccl = a;
     return true;
@@ -101,6 +103,8 @@ struct sph_multi {
     bool copyExchange = false;                  // one process: neighbours' buffers are copied directly (cudaMemcpyPeerAsync)
                                                 // instead of ncclSend/ncclRecv -- also what lets several slabs share one GPU
     long long steps = 0;
+    int n = 0;                                  // particles of the whole system (sph_multi_set_state)
+    int recutEvery = 0, recuts = 0;             // re-cut the slabs every so many steps (0: never); how often it happened
     unsigned long long bytesSent = 0;
     std::string err;
 };
@@ -244,6 +248,32 @@ int load_slab(sph_multi* m, MultiRank& r, const float* d_records, int count)
     MCU(m, cudaStreamSynchronize(s->stream));
     s->stepped = false;
     r.owned = count;
+    return SPH_OK;
+}
+
+// message sections from the fullest layer: every slab agrees on them (fixed-size messages, counts in the header row).
+// Returns whether the buffers must be (re)allocated.
+bool message_geometry(sph_multi* m, long long fullest)
+{
+    const char* se = getenv("SPH_B200_SLAB_SAFETY");
+    const double safety = se ? atof(se) : 1.5;
+    // (a safety below 1 is a test aid: no slack, so that the overflow report can be exercised)
+    const int capB = (int)std::min<long long>(std::max<long long>((long long)(fullest * safety), 64) + (safety >= 1.0 ? 8192 : 0), 0x3fffffff);
+    const int capL = safety >= 1.0 ? std::max(capB / 4, 4096) : std::max(capB / 4, 16);
+    const bool resize = capB > m->capB || capL > m->capL;       // buffers only ever grow
+    if (resize) { m->capB = std::max(capB, m->capB);  m->capL = std::max(capL, m->capL); }
+    return resize;
+}
+
+// slab r takes the layers the current cuts give it; message buffers follow the current geometry
+int configure_rank(sph_multi* m, MultiRank& r, bool resize)
+{
+    MCU(m, cudaSetDevice(r.device));
+    r.zLo = m->cuts[r.rank];  r.zHi = m->cuts[r.rank + 1];
+    r.hasLower = r.rank > 0;  r.hasUpper = r.rank < m->world - 1;
+    if (sph_slab_configure(r.s, r.zLo, r.zHi, r.hasLower, r.hasUpper) != SPH_OK)
+        return mfail(m, SPH_ERR_PARAMS, "slab %d: %s", r.rank, sph_last_error(r.s));
+    if (resize || !r.msgDown) if (int rc = alloc_messages(m, r)) return rc;
     return SPH_OK;
 }
 
@@ -425,6 +455,7 @@ extern "C" int sph_multi_set_params(sph_multi_t* m, const struct SimParams* p)
 extern "C" int sph_multi_set_state(sph_multi_t* m, const float* pos, const float* vel, int n, const int* cuts)
 {
     if (!m || !pos || !vel || n < 1) return SPH_ERR_ARG;
+    m->n = n;
     const SimParams& P = m->par;
     const int gz = (int)P.gridSize.z, W = m->world;
     std::vector<int> zc(n);
@@ -440,25 +471,16 @@ extern "C" int sph_multi_set_state(sph_multi_t* m, const float* pos, const float
     if (m->cuts.front() != 0 || m->cuts.back() != gz) return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: cuts must run from 0 to gridSize.z");
     for (int r = 0; r < W; r++) if (m->cuts[r + 1] - m->cuts[r] < 1) return mfail(m, SPH_ERR_ARG, "sph_multi_set_state: empty slab %d", r);
 
-    // message sections from the fullest layer: every slab agrees on them (fixed-size messages, counts in the header row)
     const long long fullest = *std::max_element(hist.begin(), hist.end());
-    const char* se = getenv("SPH_B200_SLAB_SAFETY");
-    const double safety = se ? atof(se) : 1.5;
-    // (a safety below 1 is a test aid: no slack, so that the overflow report can be exercised)
-    const int capB = (int)std::min<long long>(std::max<long long>((long long)(fullest * safety), 64) + (safety >= 1.0 ? 8192 : 0), 0x3fffffff);
-    const int capL = safety >= 1.0 ? std::max(capB / 4, 4096) : std::max(capB / 4, 16);
-    const bool resize = capB != m->capB || capL != m->capL;
-    m->capB = capB;  m->capL = capL;
+    const bool resize = message_geometry(m, fullest);
+    const int capB = m->capB, capL = m->capL;
+    (void)capL;
 
     std::vector<float> rec;
     for (MultiRank& r : m->ranks) {
         sph_system* s = r.s;
         MCU(m, cudaSetDevice(r.device));
-        r.zLo = m->cuts[r.rank];  r.zHi = m->cuts[r.rank + 1];
-        r.hasLower = r.rank > 0;  r.hasUpper = r.rank < W - 1;
-        if (sph_slab_configure(s, r.zLo, r.zHi, r.hasLower, r.hasUpper) != SPH_OK)
-            return mfail(m, SPH_ERR_PARAMS, "slab %d: %s", r.rank, sph_last_error(s));
-        if (resize || !r.msgDown) if (int rc = alloc_messages(m, r)) return rc;
+        if (int rc = configure_rank(m, r, resize)) return rc;
         long long mine = 0;
         for (int z = r.zLo; z < r.zHi; z++) mine += hist[z];
         // a step's work set: last step's ghosts below + owned + arrivals + new ghosts on both sides (+ own leavers)
@@ -493,6 +515,8 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
     const int capL = m->capL, capB = m->capB;
     const bool multi = m->world > 1;
     for (int step = 0; step < nsteps; step++) {
+        if (m->recutEvery > 0 && m->steps > 0 && m->steps % m->recutEvery == 0)
+            if (int rc = sph_multi_recut(m)) return rc;
         // ---- A: edge layers + particle messages; B: everything else, overlapping exchange 1
         for (MultiRank& r : m->ranks) {
             sph_system* s = r.s;
@@ -709,3 +733,117 @@ extern "C" int sph_multi_phase_ms(sph_multi_t* m, int local, int enable, float* 
     m->phaseTiming = enable != 0;
     return SPH_OK;
 }
+
+// ---- re-cutting the slabs: the cuts balance the particle counts at set_state time; a flow that
+// piles the fluid up at one end (a wave running down the tank) unbalances them.  The slabs are synchronised, the layer
+// histogram of the CURRENT state gives new cuts, particles move to their new owners, every slab is re-sorted.  Results
+// do not depend on where the cuts are, so a run with re-cuts equals a run without, bit for bit.
+static int recut_one_process(sph_multi* m)
+{
+    std::vector<float> pos((size_t)m->n * 4), vel((size_t)m->n * 4);
+    int written = 0;
+    if (int rc = sph_multi_get_state(m, pos.data(), vel.data(), nullptr, nullptr, m->n, &written)) return rc;
+    if (written != m->n) return mfail(m, SPH_ERR_STATE, "sph_multi_recut: %d of %d particles found", written, m->n);
+    return sph_multi_set_state(m, pos.data(), vel.data(), m->n, nullptr);
+}
+
+static int recut_one_process_per_slab(sph_multi* m)
+{
+    MultiRank& r = m->ranks[0];
+    sph_system* s = r.s;
+    const SimParams& P = m->par;
+    const int W = m->world, gz = (int)P.gridSize.z, me = r.rank;
+    if (int rc = sync_rank(m, r)) return rc;
+    const int first = (int)r.hostSt[SD_FIRST], count = (int)(r.hostSt[SD_END] - r.hostSt[SD_FIRST]);
+    float* stage = reinterpret_cast<float*>(s->nlist);
+    std::vector<float> rec((size_t)std::max(count, 1) * kRecFloats);
+    if (count > 0) {
+        sph_launch_slab_export(sph_launcher(s), s->pos[s->cur], s->vel, s->idx[s->cur], nullptr, nullptr, first, count, stage);
+        MCU(m, cudaMemcpyAsync(rec.data(), stage, (size_t)count * kRecFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        MCU(m, cudaStreamSynchronize(s->stream));
+    }
+    // global layer histogram (the only collectives of the driver: two per re-cut, none on the step path)
+    std::vector<long long> hist(gz, 0);
+    std::vector<int> zc(std::max(count, 1));
+    for (int k = 0; k < count; k++) {
+        int z = host_z_cell(P, rec[(size_t)k * kRecFloats + 2]);
+        zc[k] = z = std::min(std::max(z, 0), gz - 1);
+        hist[z]++;
+    }
+    long long* dScratch = nullptr;
+    const size_t scratchWords = (size_t)std::max(gz, W * W) + W;
+    MCU(m, cudaMalloc((void**)&dScratch, scratchWords * sizeof(long long)));
+    auto done = [&](int rc) { cudaFree(dScratch);  return rc; };
+    MCU(m, cudaMemcpyAsync(dScratch, hist.data(), (size_t)gz * sizeof(long long), cudaMemcpyHostToDevice, r.xs));
+    MNCCL(m, g_nccl.AllReduce(dScratch, dScratch, (size_t)gz, ncclInt64, ncclSum, r.comm, r.xs));
+    MCU(m, cudaMemcpyAsync(hist.data(), dScratch, (size_t)gz * sizeof(long long), cudaMemcpyDeviceToHost, r.xs));
+    MCU(m, cudaStreamSynchronize(r.xs));
+    if (!cut_layers(hist, W, 2, m->cuts)) return done(mfail(m, SPH_ERR_STATE, "sph_multi_recut: %d z layers are too few for %d slabs", gz, W));
+    const bool resize = message_geometry(m, *std::max_element(hist.begin(), hist.end()));
+
+    // bin the records by new owner; counts to everybody
+    std::vector<long long> sendCnt(W, 0), off(W + 1, 0);
+    std::vector<int> dest(std::max(count, 1));
+    for (int k = 0; k < count; k++) {
+        int d = (int)(std::upper_bound(m->cuts.begin(), m->cuts.end(), zc[k]) - m->cuts.begin()) - 1;
+        dest[k] = d = std::min(std::max(d, 0), W - 1);
+        sendCnt[d]++;
+    }
+    for (int d = 0; d < W; d++) off[d + 1] = off[d] + sendCnt[d];
+    std::vector<float> binned((size_t)std::max(count, 1) * kRecFloats);
+    {
+        std::vector<long long> at(off.begin(), off.end() - 1);
+        for (int k = 0; k < count; k++)
+            memcpy(binned.data() + (size_t)at[dest[k]]++ * kRecFloats, rec.data() + (size_t)k * kRecFloats, kRecFloats * sizeof(float));
+    }
+    std::vector<long long> all((size_t)W * W, 0);
+    long long* dSend = dScratch + (size_t)W * W;
+    MCU(m, cudaMemcpyAsync(dSend, sendCnt.data(), (size_t)W * sizeof(long long), cudaMemcpyHostToDevice, r.xs));
+    MNCCL(m, g_nccl.AllGather(dSend, dScratch, (size_t)W, ncclInt64, r.comm, r.xs));
+    MCU(m, cudaMemcpyAsync(all.data(), dScratch, (size_t)W * W * sizeof(long long), cudaMemcpyDeviceToHost, r.xs));
+    MCU(m, cudaStreamSynchronize(r.xs));
+    long long incoming = 0;
+    std::vector<long long> roff(W + 1, 0);
+    for (int p = 0; p < W; p++) { const long long c = p == me ? 0 : all[(size_t)p * W + me];  roff[p + 1] = roff[p] + c;  incoming += c; }
+    const long long kept = sendCnt[me], total = kept + incoming;
+    if (total > r.capacity) return done(mfail(m, SPH_ERR_STATE, "sph_multi_recut: slab %d would own %lld particles, capacity %d", me, total, r.capacity));
+
+    // particles travel device to device: everything leaves from the staging area, the new owned set is assembled in a
+    // temporary buffer (kept block first, then one block per sender)
+    float* dNew = nullptr;
+    MCU(m, cudaMalloc((void**)&dNew, (size_t)std::max<long long>(total, 1) * kRecFloats * sizeof(float)));
+    auto done2 = [&](int rc) { cudaFree(dNew);  return done(rc); };
+    if (count > 0) MCU(m, cudaMemcpyAsync(stage, binned.data(), (size_t)count * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, r.xs));
+    if (kept > 0) MCU(m, cudaMemcpyAsync(dNew, stage + (size_t)off[me] * kRecFloats, (size_t)kept * kRecFloats * sizeof(float), cudaMemcpyDeviceToDevice, r.xs));
+    MNCCL(m, g_nccl.GroupStart());
+    for (int p = 0; p < W; p++) {
+        if (p == me) continue;
+        if (sendCnt[p] > 0) MNCCL(m, g_nccl.Send(stage + (size_t)off[p] * kRecFloats, (size_t)sendCnt[p] * kRecFloats * sizeof(float), ncclChar, p, r.comm, r.xs));
+        const long long c = all[(size_t)p * W + me];
+        if (c > 0) MNCCL(m, g_nccl.Recv(dNew + (size_t)(kept + roff[p]) * kRecFloats, (size_t)c * kRecFloats * sizeof(float), ncclChar, p, r.comm, r.xs));
+    }
+    MNCCL(m, g_nccl.GroupEnd());
+    MCU(m, cudaStreamSynchronize(r.xs));
+    if (int rc = configure_rank(m, r, resize)) return done2(rc);
+    return done2(load_slab(m, r, dNew, (int)total));
+}
+
+extern "C" int sph_multi_recut(sph_multi_t* m)
+{
+    if (!m) return SPH_ERR_ARG;
+    if (!m->haveState) return mfail(m, SPH_ERR_STATE, "sph_multi_recut: no state");
+    int rc = SPH_OK;
+    if (m->world > 1) rc = (int)m->ranks.size() == m->world ? recut_one_process(m) : recut_one_process_per_slab(m);
+    if (rc == SPH_OK) m->recuts++;
+    return rc;
+}
+
+/* every `steps` steps sph_multi_step re-cuts the slabs before stepping on (0: never) */
+extern "C" int sph_multi_set_recut_interval(sph_multi_t* m, int steps)
+{
+    if (!m || steps < 0) return SPH_ERR_ARG;
+    m->recutEvery = steps;
+    return SPH_OK;
+}
+
+extern "C" int sph_multi_recut_count(sph_multi_t* m) { return m ? m->recuts : 0; }

@@ -88,7 +88,7 @@ ABI_SYMBOLS = (
     "sph_multi_unique_id", "sph_multi_create", "sph_multi_create_rank", "sph_multi_destroy", "sph_multi_last_error",
     "sph_multi_set_params", "sph_multi_set_state", "sph_multi_step", "sph_multi_sync", "sph_multi_get_state",
     "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info", "sph_multi_fetch_owned", "sph_multi_put_owned",
-    "sph_multi_phase_ms",
+    "sph_multi_phase_ms", "sph_multi_recut", "sph_multi_set_recut_interval", "sph_multi_recut_count",
 )
 
 
@@ -165,6 +165,9 @@ def load() -> C.CDLL:
     lib.sph_multi_fetch_owned.argtypes = [vp, ci, vp, ci, ip]
     lib.sph_multi_put_owned.argtypes = [vp, ci, vp, ci]
     lib.sph_multi_phase_ms.argtypes = [vp, ci, ci, vp]
+    lib.sph_multi_recut.argtypes = [vp]
+    lib.sph_multi_set_recut_interval.argtypes = [vp, ci]
+    lib.sph_multi_recut_count.argtypes = [vp]
     lib.sph_multi_local_slabs.argtypes = [vp]
     lib.sph_multi_handle.argtypes = [vp, ci]
     lib.sph_multi_handle.restype = vp
@@ -383,6 +386,15 @@ class MultiSystem:
         out = np.zeros(11, np.float32)
         self._check(self.lib.sph_multi_phase_ms(self.h, local, 1, _ptr(out)), "sph_multi_phase_ms")
         return dict(zip(self.PHASES, [round(float(x), 4) for x in out]))
+
+    def recut(self):
+        self._check(self.lib.sph_multi_recut(self.h), "sph_multi_recut")
+
+    def set_recut_interval(self, steps: int):
+        self._check(self.lib.sph_multi_set_recut_interval(self.h, steps), "sph_multi_set_recut_interval")
+
+    def recut_count(self) -> int:
+        return int(self.lib.sph_multi_recut_count(self.h))
 
     def local_slabs(self) -> int:
         return int(self.lib.sph_multi_local_slabs(self.h))

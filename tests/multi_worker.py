@@ -17,6 +17,7 @@ def main():
     from test_multi import stir
 
     title, steps, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    recut = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -28,6 +29,7 @@ def main():
     pos, vel = s.host_arrays()
     m = lib.MultiSystem(s.params, capacity_per_slab=s.n, rank=rank, world=world, unique_id=ids[0], device=local)
     m.set_state(pos, stir(vel))
+    m.set_recut_interval(recut)
     for _ in range(steps):
         s.UpdateEmitter()
         m.set_params(s.params)
@@ -41,7 +43,7 @@ def main():
             mask = ~np.isnan(q[2])
             P[mask], V[mask], D[mask] = q[0][mask], q[1][mask], q[2][mask]
         assert sum(q[3] for q in parts) == s.n and not np.isnan(D).any()
-        np.savez(out, pos=P, vel=V, dens=D)
+        np.savez(out, pos=P, vel=V, dens=D, recuts=m.recut_count())
     m.close()
     dist.barrier()
     dist.destroy_process_group()

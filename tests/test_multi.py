@@ -36,7 +36,7 @@ def single_gpu_run(title, steps):
     return out
 
 
-def multi_run(title, steps, slabs, monkeypatch=None, variant=None, check_every=0):
+def multi_run(title, steps, slabs, monkeypatch=None, variant=None, check_every=0, recut_every=0):
     s = host.CSph(device=-1)                      # scene + initial state on the host only
     s.select_scene(title)
     par = s.params
@@ -45,6 +45,7 @@ def multi_run(title, steps, slabs, monkeypatch=None, variant=None, check_every=0
     n = s.n
     m = lib.MultiSystem(par, capacity_per_slab=int(n / slabs * 1.6) + 40000, devices=[0] * slabs)
     m.set_state(pos, vel)
+    m.set_recut_interval(recut_every)
     owned0 = m.info()["owned"]
     assert sum(owned0) == n
     for k in range(steps):
@@ -55,6 +56,7 @@ def multi_run(title, steps, slabs, monkeypatch=None, variant=None, check_every=0
             m.sync()
     p, v, d, _, written = m.get_state(density=True)
     info = m.info()
+    info["recuts"] = m.recut_count()
     m.close()
     assert written == n and sum(info["owned"]) == n
     return (p, v, d), owned0, info
@@ -77,6 +79,15 @@ def test_multi_driver_other_pair_variants(monkeypatch, variant):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", variant)
     got, _, _ = multi_run("mini waves", 6, 3)
     ref = single_gpu_run("mini waves", 6)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+def test_multi_driver_recut_keeps_the_results(monkeypatch):
+    """Re-cutting the slabs every three steps changes who owns what, never the result."""
+    got, _, info = multi_run("mini waves", 10, 3, recut_every=3)
+    assert info["recuts"] == 3
+    ref = single_gpu_run("mini waves", 10)
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
 
@@ -119,10 +130,11 @@ def test_multi_driver_nccl_two_processes(tmp_path):
     out = tmp_path / "multi.npz"
     steps = 8
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), str(ROOT / "tests" / "multi_worker.py"), "wave tank 256k", str(steps), str(out)]
+           "--master-port", str(free_port()), str(ROOT / "tests" / "multi_worker.py"), "wave tank 256k", str(steps), str(out), "3"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     got = np.load(out)
+    assert int(got["recuts"]) == 2, "the worker re-cuts every three steps (NCCL all-reduce / all-gather + send/recv)"
     ref = single_gpu_run("wave tank 256k", steps)
     assert np.array_equal(got["pos"], ref[0]) and np.array_equal(got["vel"], ref[1]) and np.array_equal(got["dens"], ref[2])
 
