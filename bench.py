@@ -448,6 +448,42 @@ def run_ours_multi(args) -> dict | None:
 
 
 
+def scaling_base(steps: int, warmup: int) -> dict:
+    """The N=1 point of the weak-scaling curve on the SAME path the N>1 runs take: 'wave tank 8M' as one slab of the C++
+    multi-GPU driver (no neighbours, so no exchange) -- so that 1 -> N compares one code path on one scene family."""
+    import torch
+    from pibiti_b200 import host, lib
+    title = "wave tank 8M"
+    s = host.CSph(device=-1)
+    s.select_scene(title)
+    pos, vel = s.host_arrays()
+    n = s.n
+    m = lib.MultiSystem(s.params, capacity_per_slab=int(n * 1.25) + 600000, devices=[0])
+    m.set_state(pos, vel)
+    del pos, vel
+    stream = torch.cuda.ExternalStream(m.stream(0))
+
+    def one_step():
+        s.UpdateEmitter()
+        m.set_params(s.params)
+        m.step(1)
+
+    for _ in range(max(warmup, 3)):
+        one_step()
+    m.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        one_step()
+    e1.record(stream)
+    m.sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    m.close()
+    return {"workload": title, "particles": n, "path": "sph_multi_* driver, one slab (the N=1 point of the slab-decomposed runs)",
+            "steps": steps, "ms_per_step": round(ms, 4), "value": n / (ms * 1e-3), "unit": UNIT}
+
+
 def _host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
@@ -621,6 +657,8 @@ def main():
     if not args.no_cpu_baseline:
         s.close()
         out["cpu_baseline"], out["parity_check"] = cpu_baseline(out["config"]["workload"])
+        if args.workload is None:
+            out["scaling_base"] = scaling_base(min(args.steps, 30), 5)
     print(json.dumps(out), flush=True)
 
 

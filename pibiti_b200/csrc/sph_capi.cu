@@ -103,7 +103,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
             // staged variant: cap candidates (32 B each in the force kernel) plus the list block in shared memory;
             // rm variant: cap = records per particle (kMax unused)
             const size_t smemNeed = tma ? (size_t)c * 32 + (size_t)k * t * 2 + 1024 : 0;
-            if (smemNeed <= prop.sharedMemPerBlockOptin && !(rm && c > 64)) {
+            if (smemNeed <= prop.sharedMemPerBlockOptin && !(rm && (c > 64 || t > 128))) {
                 s->cfg.mode = tma ? SPH_PAIR_TMA : rm ? SPH_PAIR_RM : SPH_PAIR_L1;
                 s->cfg.threads = t;  s->cfg.cap = c;  s->cfg.kMax = k;
             }
@@ -145,6 +145,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     CREATE_TRY(cudaMemsetAsync(s->velD, 0, n * sizeof(float4), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->counters, 0, 16 * sizeof(uint32_t), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->keyMax, 0, (kKeyMaxSlots + 8) * sizeof(uint32_t), s->stream));
     sph_launch_iota(launcher(s), s->idx[0], (int)n);
     CREATE_TRY(cudaStreamSynchronize(s->stream));
@@ -694,7 +695,12 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
         CU_TRY(s, cudaMemcpyAsync(s->hostInts + k, s->cellStart + cells[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaMemcpyAsync(s->hostInts + 5, s->counters + kDevWork, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(s, cudaMemcpyAsync(s->hostInts + 7, s->keyMax + kKeyMaxSlots, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->hostInts + 9, s->counters + kDevWork + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->counters + kDevWork + 2, 0, sizeof(uint32_t), s->stream));
     CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->hostInts[9])
+        return fail(s, SPH_ERR_STATE, "slab decomposition lost a particle: it moved further than one cell layer along z in a step "
+                    "(beyond the halo), or a boundary teleported it");
     // table entries at or above the scan bound were not written this step: no live key is that large, so they equal
     // the live total, which is the start of the dummy cell (always scanned)
     {

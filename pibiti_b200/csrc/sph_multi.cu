@@ -400,6 +400,17 @@ extern "C" int sph_multi_create(const struct SimParams* params, int ndev, const 
     m->copyExchange = repeated || (xe && strcmp(xe, "copy") == 0);
     if (ndev > 1 && !m->copyExchange && !load_nccl(why)) { delete m;  return mfail(nullptr, SPH_ERR_CUDA, "sph_multi_create: %s", why.c_str()); }
     int rc = create_common(m, params, capacityPerSlab);
+    if (rc == SPH_OK && ndev > 1 && m->copyExchange) {
+        // direct NVLink copies between neighbouring slabs (without peer access the copies would stage through the host)
+        for (int k = 0; k + 1 < ndev; k++) {
+            const int a = devices[k], b = devices[k + 1];
+            if (a == b) continue;
+            int ok = 0;
+            if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok) { cudaSetDevice(a);  cudaDeviceEnablePeerAccess(b, 0); }
+            if (cudaDeviceCanAccessPeer(&ok, b, a) == cudaSuccess && ok) { cudaSetDevice(b);  cudaDeviceEnablePeerAccess(a, 0); }
+            cudaGetLastError();                 // "already enabled" is fine
+        }
+    }
     if (rc == SPH_OK && ndev > 1 && !m->copyExchange) {
         std::vector<ncclComm_t> comms(ndev);
         ncclResult_t r = g_nccl.CommInitAll(comms.data(), ndev, devices);

@@ -952,7 +952,8 @@ struct RmCursor {
     }
 };
 
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_force_rm(const __grid_constant__ SimParams par, int recCap,
            const float4* __restrict__ posP, const float4* __restrict__ velD, const float4* __restrict__ velS,
            const uint32_t* __restrict__ keyS, const uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ maxCount,
@@ -1011,7 +1012,9 @@ inline size_t force_smem(const SphPairConfig& c) { return (size_t)c.cap * 32 + (
 
 void sph_pair_default_config(SphPairConfig* cfg)
 {
-    cfg->mode = SPH_PAIR_RM;  cfg->threads = 128;  cfg->cap = 24;  cfg->kMax = 48;        // rm: cap = records per particle
+    // rm: cap = records per particle.  A row of three cells is one record per 32 candidates, or one per cell where the
+    // maxParInCell truncation cuts it: 27 at most in ordinary scenes; beyond the cap a particle falls back to the walk
+    cfg->mode = SPH_PAIR_RM;  cfg->threads = 128;  cfg->cap = 32;  cfg->kMax = 48;
 }
 
 const char* sph_pair_mode_name(int mode) { return mode == SPH_PAIR_TMA ? "tma" : mode == SPH_PAIR_RM ? "rm" : "l1"; }
@@ -1088,9 +1091,14 @@ void sph_launch_force(const SphLaunch& L, const SphPairConfig& cfg, const SimPar
         if (ctaCount <= 0) return;
         blocks = ctaCount;
     } else ctaFirst = 0;
-    if (cfg.mode == SPH_PAIR_RM)
-        k_force_rm<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
-                                                         (const uint2*)nlist, ncount, velOut, first, n, ctaFirst, dev, part);
+    if (cfg.mode == SPH_PAIR_RM) {
+        static const int occ = [] { const char* e = getenv("SPH_B200_RM_FORCE_OCC");  const int v = e ? atoi(e) : 10;  return v == 8 || v == 12 ? v : 10; }();
+        auto launch = [&](auto kern) {
+            kern<<<blocks, cfg.threads, 0, L.stream>>>(par, cfg.cap, posP, velD, velS, keyS, cellStart, maxCount,
+                                                       (const uint2*)nlist, ncount, velOut, first, n, ctaFirst, dev, part);
+        };
+        if (occ == 8) launch(k_force_rm<8>);  else if (occ == 12) launch(k_force_rm<12>);  else launch(k_force_rm<10>);
+    }
     else if (cfg.mode == SPH_PAIR_TMA)
         k_force<<<blocks, cfg.threads, force_smem(cfg), L.stream>>>(par, cfg.cap, cfg.kMax, posP, velD, velS, keyS, cellStart, maxCount,
                                                                     (const uint16_t*)nlist, ncount, ctaRows, velOut, first, n);

@@ -664,6 +664,9 @@ k_slab_hash_hist(const __grid_constant__ SimParams par, const float4* __restrict
             const float4 p = pos[i];
             long long k = (long long)cell_hash(par, make_float3(p.x, p.y, p.z)) - keyOffset;
             if (k >= 0 && k < (long long)numCellsLocal) { key = (uint32_t)k;  live1 = key + 1; }
+            // a LIVE particle outside the local table moved further than the one-layer halo in a step (or was teleported):
+            // the decomposition cannot follow it, which is reported (word nDev[2], read back by sph_slab_sort), not hidden
+            else atomicOr(const_cast<uint32_t*>(nDev) + 2, 1u);
         }
         keyU[i] = key;
         rankU[i] = atomicAdd(&cellCount[key], 1u);

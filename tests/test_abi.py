@@ -68,6 +68,11 @@ def test_no_gpu_means_loud_failure_not_fallback(golden_repo_scenes):
     s = host.CSph(device=-1)
     with pytest.raises(lib.SphError):
         s.Update()
+    # ... and so does the multi-GPU driver (both shapes), with the reason in its own error channel
+    with pytest.raises(lib.SphError, match="CUDA|no CPU path"):
+        lib.MultiSystem(par, capacity_per_slab=8192, devices=[0, 0])
+    with pytest.raises(lib.SphError, match="CUDA|no CPU path"):
+        lib.MultiSystem(par, capacity_per_slab=8192, rank=0, world=1, device=0)
 
 
 def test_bad_params_rejected():

@@ -67,7 +67,7 @@ def check_integers_exact(g, o):
 # shared memory by TMA bulk copies, "l1,..." reads them through L1 (one particle per thread, index lists), "rm,..." is
 # the same walk with {bit mask, first index} neighbour records instead of index lists.  Format: mode,threads,cap,kMax
 # (rm: cap = records per particle, kMax unused)
-PAIR_VARIANTS = {"l1": "l1,128,1344,48", "tma": "tma,128,1344,48", "rm": "rm,128,24,48"}
+PAIR_VARIANTS = {"l1": "l1,128,1344,48", "tma": "tma,128,1344,48", "rm": "rm,128,32,48"}
 
 
 @pytest.mark.parametrize("variant", ["l1", "tma", "rm"])

@@ -138,7 +138,7 @@ def single_gpu_run(title, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["l1,128,1344,48", "tma,128,1344,48", "rm,128,24,48"])
+@pytest.mark.parametrize("variant", ["l1,128,1344,48", "tma,128,1344,48", "rm,128,32,48"])
 @pytest.mark.parametrize("title,ranks", [("mini waves", 2), ("mini waves", 3), ("wave tank 256k", 4)])
 def test_gpu_slabs_equal_single_gpu(title, ranks, variant, monkeypatch):
     monkeypatch.setenv("SPH_B200_PAIR_CFG", variant)
