@@ -303,6 +303,21 @@ def _multi_parity_check(dist, rank, world, local, uid_fn) -> dict:
     return res
 
 
+_CK_PRIMES = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5, 0x85EBCA77C2B2AE63,
+                       0xD6E8FEB86659FD93, 0xFF51AFD7ED558CCD, 0xC4CEB9FE1A85EC53, 0x94D049BB133111EB], dtype=np.uint64)
+
+
+def state_checksum(ids: np.ndarray, pos: np.ndarray, vel: np.ndarray, dens: np.ndarray) -> int:
+    """Order-independent 64-bit checksum of {(original index, position, velocity, density)}: bit-equal particle sets give
+    equal sums whichever slab holds which particle (a checksum of per-particle checksums, mod 2^64)."""
+    words = np.concatenate([np.ascontiguousarray(pos, np.float32).view(np.uint32).reshape(-1, 4),
+                            np.ascontiguousarray(vel, np.float32).view(np.uint32).reshape(-1, 4),
+                            np.ascontiguousarray(dens, np.float32).view(np.uint32).reshape(-1, 1)], axis=1).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = (words * _CK_PRIMES[None, :]).sum(axis=1, dtype=np.uint64)
+        return int((h * (ids.astype(np.uint64) * np.uint64(2) + np.uint64(1))).sum(dtype=np.uint64))
+
+
 def run_ours_multi(args) -> dict | None:
     """bench.py under torchrun (one process per GPU): weak scaling, 8M particles per GPU, the wave tank cut into z slabs and
     stepped by the C++ multi-GPU driver (sph_multi_*: NCCL send/recv from C++, no torch.distributed on the data path --
@@ -342,20 +357,25 @@ def run_ours_multi(args) -> dict | None:
     m.enable_phase_timing(True)                  # a dozen more event records per step, no synchronisation
     stream = torch.cuda.ExternalStream(m.stream(0))
 
+    replay = []                                  # the parameter block of every step, for the full-size check below
+
     def one_step():
         s.UpdateEmitter()                        # wave phase: identical host arithmetic on every rank
-        m.set_params(s.params)
+        par_k = s.params
+        replay.append(par_k.tobytes())
+        m.set_params(par_k)
         m.step(1)
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
         one_step()
-    m.sync()
-    dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                          # spawns nvidia-smi (tens of ms): before the barrier, or the other ranks'
+    m.sync()                                     # first exchange would wait for it inside their timed region
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.barrier()
     l0 = view.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -383,10 +403,46 @@ def run_ours_multi(args) -> dict | None:
     per_gpu = [int(c.item()) for c in counts]
     ms_total = float(ms.item())
 
-    # end to end with HOST buffers: every step uploads this rank's owned records from pinned memory and reads them back
-    e2e_steps = max(3, min(args.steps, 5))
+    # ---- full-size parity: the state after warm-up + timed steps, as a checksum over all slabs, against ONE GPU running the
+    # whole system through the same parameter blocks (the B200 holds 64M particles: ~27 GB).  Bit-exact or not at all.
     host_rec = torch.empty((m.capacity, 12), dtype=torch.float32, pin_memory=True)
     cnt = m.fetch_owned(0, host_rec.data_ptr(), m.capacity)
+    rec = host_rec.numpy()[:cnt]
+    ck = state_checksum(np.ascontiguousarray(rec[:, 8]).view(np.uint32), rec[:, 0:4], rec[:, 4:8], np.ascontiguousarray(rec[:, 9]))
+    limbs = torch.tensor([ck & 0xFFFFFFFF, ck >> 32, cnt], device="cuda", dtype=torch.int64)
+    dist.all_reduce(limbs)
+    ck_multi = (int(limbs[0].item()) + (int(limbs[1].item()) << 32)) & 0xFFFFFFFFFFFFFFFF
+    full_check = {"config": title, "particles": n, "steps": len(replay), "what": "checksum of (id, pos, vel, rho) over all slabs vs one "
+                  "GPU stepping the whole system through the same parameter blocks", "ok": None}
+    if rank == 0 and world > 1 and not os.environ.get("SPH_BENCH_SKIP_FULL_CHECK"):
+        try:
+            free_b, _ = torch.cuda.mem_get_info()
+            need = n * 520 + int(par["numCells"][0]) * 10 + (1 << 30)
+            if free_b < need:
+                full_check["skipped"] = f"single-GPU replay needs ~{need >> 30} GiB, {free_b >> 30} GiB free beside this rank's slab"
+            else:
+                s1 = host.CSph(device=-1)
+                s1.select_scene(title)
+                p1, v1 = s1.host_arrays()
+                g1 = lib.SphSystem(s1.params, local)
+                g1.set_array(lib.SPH_POS, p1)
+                g1.set_array(lib.SPH_VEL, v1)
+                del p1, v1
+                for blk in replay:
+                    g1.set_params(np.frombuffer(blk, dtype=lib.SIMPARAMS_DTYPE))
+                    g1.step(1)
+                ck_one = state_checksum(np.arange(n, dtype=np.uint32), g1.get_array(lib.SPH_POS), g1.get_array(lib.SPH_VEL),
+                                        g1.get_array(lib.SPH_DENSITY))
+                g1.close()
+                s1.close()
+                full_check.update({"ok": bool(ck_one == ck_multi and int(limbs[2].item()) == n), "checksum_slabs": f"{ck_multi:016x}",
+                                   "checksum_one_gpu": f"{ck_one:016x}"})
+        except Exception as e:                               # noqa: BLE001
+            full_check["error"] = f"{type(e).__name__}: {e}"
+    dist.barrier()
+
+    # end to end with HOST buffers: every step uploads this rank's owned records from pinned memory and reads them back
+    e2e_steps = max(3, min(args.steps, 5))
     dist.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
@@ -430,6 +486,7 @@ def run_ours_multi(args) -> dict | None:
         "phase_ms_last_step_by_rank": phases,
         "after_run": {"particles_conserved": bool(int(owned_end.item()) == n), "all_finite": bool(flags.item() == 1)},
         "parity_check": parity,
+        "parity_check_full_size": full_check if world > 1 else None,
         "roofline": None,
     }
     dom = max((k for k in ("density", "force") if k in kernel_ms), key=lambda k: kernel_ms[k], default=None)
