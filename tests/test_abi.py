@@ -138,3 +138,42 @@ def test_app_style_cpp_client_compiles_and_links_against_the_host_header(tmp_pat
     r = subprocess.run([str(exe), str(host.DEFAULT_SCENES_XML)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "scenes" in r.stdout and "update rc" in r.stdout and "update rc 0" not in r.stdout
+
+
+MULTI_GPU_CLIENT = r'''
+// What an App that holds a cSPH on SEVERAL GPUs writes (INTEGRATION.md section 5): the constructor is the only change.
+#include "sph_host.h"
+#include <cstdio>
+int main(int argc, char** argv)
+{
+    const int devices[2] = {0, 1};
+    cSPH* psys = new cSPH(argc > 1 ? argv[1] : "Scenes.xml", devices, 2);
+    psys->curScene = 0;
+    psys->UpdScene();
+    std::printf("scenes %zu, multi solver %s\n", psys->scenes.size(), psys->multiSolver() ? "up" : "absent");
+    psys->UpdateEmitter();
+    int rc = psys->Update();                         // no GPUs on this box: must fail, loudly
+    std::printf("update rc %d: %s\n", rc, psys->lastError());
+    float4* pos = psys->getArray(false);
+    int bad = pos == nullptr;
+    // the C entry points underneath
+    sph_multi_t* m = nullptr;
+    int rc2 = sph_multi_create(&psys->scn.params, 2, devices, 65536, &m);
+    std::printf("sph_multi_create rc %d: %s\n", rc2, sph_multi_last_error(nullptr));
+    if (m) sph_multi_destroy(m);
+    delete psys;
+    return (rc != 0 && rc2 != 0 && !bad) ? 0 : 1;
+}
+'''
+
+
+@pytest.mark.skipif(has_gpu(), reason="asserts the no-GPU behaviour")
+def test_multi_gpu_cpp_client_compiles_links_and_fails_loudly_without_gpus(tmp_path):
+    src, exe = tmp_path / "client_multi.cpp", tmp_path / "client_multi"
+    src.write_text(MULTI_GPU_CLIENT)
+    libdir = lib.LIB_PATH.parent
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", str(src),
+                    "-o", str(exe), f"-L{libdir}", "-lsph_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe), str(host.DEFAULT_SCENES_XML)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "multi solver absent" in r.stdout and "sph_multi_create rc 2" in r.stdout
