@@ -116,7 +116,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     { unsigned char* lb = nullptr;  ALLOC(lb, sph_pair_list_bytes(s->cfg, (int)n));  s->nlist = lb; }  ALLOC(s->ncount, n);
     ALLOC(s->ctaRows, sph_pair_blocks(s->cfg, (int)n));
     ALLOC(s->counters, 16);  ALLOC(s->keyMax, kKeyMaxSlots + 8);
-    ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, 1);
+    ALLOC(s->cellCount, C + 16);  ALLOC(s->cellStart, C + 16);  ALLOC(s->tileSums, tiles + 1);  ALLOC(s->maxCount, kMaxCountWords);
 #undef ALLOC
 
     // failures past this point release what was allocated (the handle, its buffers, stream and events)
@@ -144,7 +144,7 @@ extern "C" int sph_create(const struct SimParams* params, int device, sph_t** ou
     CREATE_TRY(cudaMemsetAsync(s->posP, 0, n * sizeof(float4), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->velD, 0, n * sizeof(float4), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->cellCount, 0, (C + 16) * sizeof(uint32_t), s->stream));
-    CREATE_TRY(cudaMemsetAsync(s->maxCount, 0, sizeof(uint32_t), s->stream));
+    CREATE_TRY(cudaMemsetAsync(s->maxCount, 0, kMaxCountWords * sizeof(uint32_t), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->counters, 0, 16 * sizeof(uint32_t), s->stream));
     CREATE_TRY(cudaMemsetAsync(s->keyMax, 0, (kKeyMaxSlots + 8) * sizeof(uint32_t), s->stream));
     sph_launch_iota(launcher(s), s->idx[0], (int)n);
@@ -248,7 +248,7 @@ static void enqueue_step(sph_system* s, int in, bool tm)
     sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, n);
     if (tm) cudaEventRecord(s->ev[2], s->stream);
     sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel,
-                           s->pos[outb], s->velS, s->idx[outb], s->keyS, n);
+                           s->pos[outb], s->velS, s->idx[outb], s->keyS, n, nullptr, s->maxCount, C);
     if (tm) cudaEventRecord(s->ev[3], s->stream);
     sph_launch_density(L, s->cfg, s->par, s->pos[outb], s->velS, s->keyS, s->cellStart, s->maxCount,
                        s->posP, s->velD, s->wantCounts ? s->counts : nullptr, s->nlist, s->ncount, s->ctaRows, 0, n);
@@ -687,7 +687,7 @@ extern "C" int sph_slab_sort(sph_t* s, int* counts3)
     sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL, s->keyMax + kKeyMaxSlots);
     if (W > 0) {
         sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, W, nDev);
-        sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W, nDev);
+        sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS, W, nDev, s->maxCount, CL);
     }
     // one read-back: five cell-table entries bracket the ghost / owned / boundary-layer ranges, plus size and overflow
     const int cells[5] = {b.lowLayers * yx, (b.lowLayers + nz) * yx, CL, (b.lowLayers + 1) * yx, (b.lowLayers + nz - 1) * yx};

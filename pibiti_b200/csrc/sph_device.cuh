@@ -44,7 +44,12 @@ void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t*
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
                             const float4* posIn, const float4* velIn,
                             float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n,
-                            const uint32_t* nDev = nullptr);     // nDev: element count read on the device (n = launch bound)
+                            const uint32_t* nDev = nullptr,      // nDev: element count read on the device (n = launch bound)
+                            const uint32_t* big = nullptr, int realCells = 0);   // big = the maxCount block of sph_launch_scan:
+                                                                 // cells it listed as big are ranked by a CTA each
+// layout of the `maxCount` block the scan fills: [0] largest real cell, [kBigCount] cells with more than kBigCell entries,
+// [kBigList ..] their indices (kBigCap at most; beyond that the list is ignored and every cell takes the per-entry path)
+static const int kBigCell = 64, kBigCount = 1, kBigList = 2, kBigCap = 4094, kMaxCountWords = kBigList + kBigCap;
 void sph_launch_iota(const SphLaunch& L, uint32_t* idx, int n);
 // original-order accessors: out[idx[j] - start] = src[j]  /  dst[j] = in[idx[j] - start]
 void sph_launch_unpermute4(const SphLaunch& L, const float4* src, const uint32_t* idx, float4* out, int start, int count, int n);

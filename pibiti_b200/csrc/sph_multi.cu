@@ -193,7 +193,7 @@ void enqueue_sort(MultiRank& r)
     sph_launch_scan(L, s->cellCount, s->cellStart, s->tileSums, s->maxCount, CL + 1, CL, s->keyMax + kKeyMaxSlots);
     sph_launch_bucket(L, s->keyU, s->rankU, s->idx[in], s->cellStart, s->pairT, r.capacity, st + SD_WORK);
     sph_launch_rank_gather(L, s->pairT, s->keyU, s->cellStart, s->pos[in], s->vel, s->pos[outb], s->velS, s->idx[outb], s->keyS,
-                           r.capacity, st + SD_WORK);
+                           r.capacity, st + SD_WORK, s->maxCount, CL);
     const int lo = b.lowLayers;
     const int cells[7] = {lo * yx, (lo + nz) * yx, CL, (lo + 1) * yx, (lo + nz - 1) * yx,
                           (lo + std::min(2, nz)) * yx, (lo + std::max(nz - 2, 0)) * yx};

@@ -298,7 +298,7 @@ k_scan_tiles(uint32_t* __restrict__ tileSums, int numTiles, uint32_t* __restrict
 {
     __shared__ uint32_t total;
     uint32_t carry = 0;
-    if (threadIdx.x == 0) *maxCount = 0;
+    if (threadIdx.x == 0) { maxCount[0] = 0;  maxCount[kBigCount] = 0; }
     for (int base = 0; base < numTiles; base += 4096) {
         const int i0 = base + threadIdx.x * 16;
         uint32_t v[16], s = 0;
@@ -339,7 +339,17 @@ k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const
         }
     }
     #pragma unroll
-    for (int k = 0; k < 16; k++) { s += c[k]; if (base + k < maxCells) mx = max(mx, c[k]); }
+    for (int k = 0; k < 16; k++) {
+        s += c[k];
+        if (base + k < maxCells) {
+            mx = max(mx, c[k]);
+            // a cell too full for the per-entry counting of k_rank_gather goes on the list k_rank_big_cells works off
+            if (c[k] > (uint32_t)kBigCell) {
+                const uint32_t at = atomicAdd(maxCount + kBigCount, 1u);
+                if (at < (uint32_t)kBigCap) maxCount[kBigList + at] = (uint32_t)(base + k);
+            }
+        }
+    }
     uint32_t ex = block_excl_scan_256(s, &total) + tileSums[blockIdx.x];
     uint32_t o[16];
     #pragma unroll
@@ -385,13 +395,16 @@ __global__ void __launch_bounds__(256)
 k_rank_gather(const uint2* __restrict__ pairT, const uint32_t* __restrict__ keyU, const uint32_t* __restrict__ cellStart,
               const float4* __restrict__ posIn, const float4* __restrict__ velIn,
               float4* __restrict__ posOut, float4* __restrict__ velOut,
-              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, int n, const uint32_t* __restrict__ nDev)
+              uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, int n, const uint32_t* __restrict__ nDev,
+              const uint32_t* __restrict__ big, int realCells)
 {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= (nDev ? (int)*nDev : n)) return;
     uint2 me = pairT[d];
     uint32_t key = keyU[me.x];
     uint32_t s = cellStart[key], e = cellStart[key + 1];
+    // cells on the big-cell list (more than kBigCell entries) are ranked by a whole CTA each, k_rank_big_cells
+    if (big && e - s > (uint32_t)kBigCell && key < (uint32_t)realCells && __ldg(big + kBigCount) <= (uint32_t)kBigCap) return;
     uint32_t r = 0;
     if (me.y == kDeadIndex) r = (uint32_t)d - s;            // slab mode: retired slots, order irrelevant
     else for (uint32_t t = s; t < e; t++) r += (pairT[t].y < me.y) ? 1u : 0u;
@@ -401,6 +414,45 @@ k_rank_gather(const uint2* __restrict__ pairT, const uint32_t* __restrict__ keyU
     velOut[f] = v;
     idxOut[f] = me.y;
     keyS[f] = key;
+}
+
+// The same stable rank + gather for the cells on the big-cell list: one CTA per cell, the original indices of the cell
+// staged through shared memory in tiles, every thread counting for one entry at a time.  Counting costs n^2 / 256 per
+// thread instead of n^2 / 1 (a cell holds a handful of particles in a healthy fluid; this is for the pile-up that a
+// diverging run or a degenerate initial state produces, where the per-entry loop would take seconds).
+__global__ void __launch_bounds__(256)
+k_rank_big_cells(const uint2* __restrict__ pairT, const uint32_t* __restrict__ cellStart,
+                 const float4* __restrict__ posIn, const float4* __restrict__ velIn,
+                 float4* __restrict__ posOut, float4* __restrict__ velOut,
+                 uint32_t* __restrict__ idxOut, uint32_t* __restrict__ keyS, const uint32_t* __restrict__ big)
+{
+    __shared__ uint32_t tile[1024];
+    const uint32_t listed = min(__ldg(big + kBigCount), (uint32_t)kBigCap);
+    if (__ldg(big + kBigCount) > (uint32_t)kBigCap) return;             // list overflowed: k_rank_gather did everything
+    for (uint32_t b = blockIdx.x; b < listed; b += gridDim.x) {
+        const uint32_t key = __ldg(big + kBigList + b);
+        const uint32_t s = cellStart[key], e = cellStart[key + 1];
+        for (uint32_t chunk = s; chunk < e; chunk += blockDim.x) {
+            const uint32_t d = chunk + threadIdx.x;
+            const bool have = d < e;
+            const uint2 me = have ? pairT[d] : make_uint2(0u, 0u);
+            uint32_t r = 0;
+            for (uint32_t t0 = s; t0 < e; t0 += 1024u) {
+                const uint32_t m = min(1024u, e - t0);
+                __syncthreads();
+                for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) tile[k] = pairT[t0 + k].y;
+                __syncthreads();
+                if (have) for (uint32_t k = 0; k < m; k++) r += (tile[k] < me.y) ? 1u : 0u;
+            }
+            if (have) {
+                const uint32_t f = s + r;
+                posOut[f] = posIn[me.x];
+                velOut[f] = velIn[me.x];
+                idxOut[f] = me.y;
+                keyS[f] = key;
+            }
+        }
+    }
 }
 
 __global__ void k_iota(uint32_t* idx, int n)
@@ -957,10 +1009,16 @@ void sph_launch_bucket(const SphLaunch& L, const uint32_t* keyU, const uint32_t*
 
 void sph_launch_rank_gather(const SphLaunch& L, const uint2* pairT, const uint32_t* keyU, const uint32_t* cellStart,
                             const float4* posIn, const float4* velIn,
-                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n, const uint32_t* nDev)
+                            float4* posOut, float4* velOut, uint32_t* idxOut, uint32_t* keyS, int n, const uint32_t* nDev,
+                            const uint32_t* big, int realCells)
 {
-    k_rank_gather<<<blocks_for(n, 256), 256, 0, L.stream>>>(pairT, keyU, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, n, nDev);
+    k_rank_gather<<<blocks_for(n, 256), 256, 0, L.stream>>>(pairT, keyU, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, n, nDev,
+                                                            big, realCells);
     SPH_COUNT(L);
+    if (big) {
+        k_rank_big_cells<<<296, 256, 0, L.stream>>>(pairT, cellStart, posIn, velIn, posOut, velOut, idxOut, keyS, big);
+        SPH_COUNT(L);
+    }
 }
 
 void sph_launch_iota(const SphLaunch& L, uint32_t* idx, int n)

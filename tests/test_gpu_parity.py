@@ -677,3 +677,31 @@ def test_checkpoint_resumes_into_an_object_on_another_scene(tmp_path):
     bad.write_bytes(bytes(raw))
     with pytest.raises(Exception):
         t.LoadState(bad)
+
+
+@pytest.mark.parametrize("variant", ["rm", "l1"])
+def test_pile_up_cells_take_the_big_cell_rank_path(oracle_any, monkeypatch, variant):
+    """Cells with more than 64 entries are ranked by a whole CTA each (k_rank_big_cells) instead of the per-entry counting
+    loop: a pile-up of 700 and one of 90 particles inside single cells must still give the reference's stable order,
+    the truncated neighbour walk (maxParInCell) and densities / velocities within the bar."""
+    monkeypatch.setenv("SPH_B200_PAIR_CFG", PAIR_VARIANTS[variant])
+    s, g, o, par = start("mini box", oracle_any)
+    pos, vel = s.host_arrays()
+    rng = np.random.Generator(np.random.PCG64(5))
+    cs = np.asarray(par["cellSize"][0], np.float32)
+    wmin = np.asarray(par["worldMin"][0], np.float32)
+    for first, count, cell in ((1000, 700, (9, 7, 9)), (4000, 90, (12, 7, 9))):
+        lo = wmin + cs * np.asarray(cell, np.float32)
+        pos[first:first + count, :3] = (lo + cs * rng.uniform(0.05, 0.95, (count, 3))).astype(np.float32)
+    for q in (g, o):
+        q.set_array(0, pos)
+        q.set_array(1, vel)
+    g.step(1)
+    o.step(1)
+    check_integers_exact(g, o)
+    assert int(np.bincount(g.dump(lib.DUMP_SORTED_PAIRS)[:, 0]).max()) > 64
+    dg, do = g.dump(lib.DUMP_DENSITY), o.dump(5)
+    assert np.all(np.abs(dg - do) <= REL * np.abs(do) + 1e-30)
+    vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
+    assert np.all(np.abs(vg - vo) <= REL * max(float(np.abs(vo[:, :3]).max()), 1e-3))
+    o.close()

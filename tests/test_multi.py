@@ -159,3 +159,40 @@ def test_csph_with_a_device_list_equals_one_device():
         return out
     one, three = run(None), run([0, 0, 0])
     assert np.array_equal(one[0], three[0]) and np.array_equal(one[1], three[1])
+
+
+def test_fetch_put_owned_round_trip_is_transparent():
+    """The per-process host accessors of the one-process-per-GPU shape (what bench.py's end-to-end leg uses): fetching a slab's
+    owned records to the host and putting them back between steps does not change the trajectory."""
+    import torch
+    s = host.CSph(device=-1)
+    s.select_scene("mini waves")
+    pos, vel = s.host_arrays()
+    vel = stir(vel)
+    m = lib.MultiSystem(s.params, capacity_per_slab=s.n, devices=[0, 0])
+    m.set_state(pos, vel)
+    buf = torch.empty((s.n, 12), dtype=torch.float32, pin_memory=True)
+    for k in range(6):
+        s.UpdateEmitter()
+        m.set_params(s.params)
+        m.step(1)
+        if k % 2 == 1:
+            for local in range(2):
+                cnt = m.fetch_owned(local, buf.data_ptr(), s.n)
+                assert 0 < cnt < s.n
+                ids = buf.numpy()[:cnt, 8].copy().view(np.uint32)
+                assert len(np.unique(ids)) == cnt
+                m.put_owned(local, buf.data_ptr(), cnt)
+    p, v, written = m.get_state()
+    m.close()
+    ref = single_gpu_run("mini waves", 6)
+    assert written == s.n and np.array_equal(p, ref[0]) and np.array_equal(v, ref[1])
+
+
+def test_multi_driver_with_obstacles_and_collider():
+    """Height map / rotor obstacles and the sphere collider run behind the force passes of every slab."""
+    for title in ("mini heightmap XZ", "mini collider accel"):
+        got, _, _ = multi_run(title, 5, 2)
+        ref = single_gpu_run(title, 5)
+        for a, b, what in zip(got, ref, ("positions", "velocities", "densities")):
+            assert np.array_equal(a, b), f"{title}: {what} differ"
