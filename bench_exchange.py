@@ -1,5 +1,6 @@
-"""A/B of the two exchange paths of the multi-GPU driver in ONE process: ncclSend/ncclRecv (ncclCommInitAll) against direct
-peer copies (cudaMemcpyPeerAsync over NVLink), same scene, same steps.  Prints one JSON line with ms/step and the phase
+"""A/B/C of the exchange paths of the multi-GPU driver in ONE process: ncclSend/ncclRecv (ncclCommInitAll), direct peer copies
+(cudaMemcpyPeerAsync over NVLink) and peer STORES (the packing kernels write the neighbours' inboxes themselves: no copy,
+only the live records travel), same scene, same steps.  Prints one JSON line with ms/step and the phase
 profile of every slab for both.  `python bench_exchange.py --gpus 2 --steps 50`."""
 from __future__ import annotations
 
@@ -61,7 +62,7 @@ def main():
     ap.add_argument("--workload", default=None)
     a = ap.parse_args()
     title = a.workload or {2: "wave tank 16M", 4: "wave tank 32M", 8: "wave tank 64M"}[a.gpus]
-    res = [run(mode, a.gpus, a.steps, a.warmup, title) for mode in ("nccl", "copy")]
+    res = [run(mode, a.gpus, a.steps, a.warmup, title) for mode in ("nccl", "copy", "peer")]
     print(json.dumps({"workload": title, "gpus": a.gpus, "steps": a.steps, "shape": "one process, one host thread", "runs": res}))
 
 

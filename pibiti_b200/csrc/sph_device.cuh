@@ -102,7 +102,9 @@ void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams
                                              uint32_t* st, int bound /* threads: >= particles of the two-layer edge regions */,
                                              int zLo, int zHi, int hasLower, int hasUpper,
                                              void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
-                                             uint32_t* headDown, uint32_t* headUp);
+                                             uint32_t* headDown, uint32_t* headUp,
+                                             void* peerDown = nullptr, void* peerUp = nullptr /* peer-store exchange: the
+                                             neighbours' inboxes (whole messages, header row first), written over NVLink */);
 void sph_launch_slab_interior_hist(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
                                    uint32_t* keyU, uint32_t* rankU, uint32_t* cellCount, uint32_t* st, int bound,
                                    long long keyOffset, int numCellsLocal, uint32_t ownedLo, uint32_t ownedHi,

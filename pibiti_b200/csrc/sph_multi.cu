@@ -18,6 +18,9 @@
 //   S     density of the owned particles, rho,p rows of the two boundary layers                      k_density_*, k_slab_pack_dp
 //   X     exchange 2: rho,p rows                                                                     -- overlaps the interior force
 //   S     force of the CTAs without ghost neighbours; then the received rows, then the remaining CTAs
+// With one process holding both ends the exchange can also be direct peer copies (SPH_B200_MULTI_XCHG=copy) or no copy at
+// all (=peer): the packing kernels store leavers, boundary copies and rho,p rows straight into the neighbours' inboxes over
+// NVLink and the receivers wait for the SENDERS' kernels -- only the live records travel.
 // Exchanges are nearest-neighbour only; there is no collective on the data path.  NCCL is loaded at run time
 // (libnccl.so.2), so the single-GPU entry points do not depend on it.
 #include "sph_internal.cuh"
@@ -102,6 +105,8 @@ struct sph_multi {
     bool phaseTiming = false;                   // record the phase events (a handful of event records per step)
     bool copyExchange = false;                  // one process: neighbours' buffers are copied directly (cudaMemcpyPeerAsync)
                                                 // instead of ncclSend/ncclRecv -- also what lets several slabs share one GPU
+    bool peerStores = false;                    // one process: no copy at all -- the packing kernels store straight into the
+                                                // neighbours' inboxes over NVLink (only the live records travel)
     long long steps = 0;
     int n = 0;                                  // particles of the whole system (sph_multi_set_state)
     int recutEvery = 0, recuts = 0;             // re-cut the slabs every so many steps (0: never); how often it happened
@@ -291,7 +296,11 @@ int create_common(sph_multi* m, const SimParams* p, int capacity)
         if (h->cfg.mode == SPH_PAIR_TMA)
             return mfail(m, SPH_ERR_PARAMS, "sph_multi: the TMA-staged pair kernels have no device-resident ranges (use rm or l1)");
         MCU(m, cudaSetDevice(r.device));
-        MCU(m, cudaStreamCreateWithFlags(&r.xs, cudaStreamNonBlocking));
+        // highest priority: the NCCL send/recv kernels must get SM slots while the interior kernels fill the GPU, or the
+        // transfer they are supposed to hide starts late (measured at N=8: 0.1 ms of waiting per step without this)
+        int prLeast = 0, prGreatest = 0;
+        MCU(m, cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        MCU(m, cudaStreamCreateWithPriority(&r.xs, cudaStreamNonBlocking, prGreatest));
         cudaEvent_t* evs[] = {&r.evA, &r.evX1, &r.evDp, &r.evX2};
         for (cudaEvent_t* e : evs) MCU(m, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (cudaEvent_t& e : r.evPhase) MCU(m, cudaEventCreate(&e));
@@ -396,8 +405,11 @@ extern "C" int sph_multi_create(const struct SimParams* params, int ndev, const 
     for (int k = 0; k < ndev; k++) { m->ranks[k].device = devices[k];  m->ranks[k].rank = k; }
     bool repeated = false;
     for (int a = 0; a < ndev; a++) for (int b = a + 1; b < ndev; b++) repeated |= devices[a] == devices[b];
-    const char* xe = getenv("SPH_B200_MULTI_XCHG");          // "copy" | "nccl"
-    m->copyExchange = repeated || (xe && strcmp(xe, "copy") == 0);
+    // one process holds both ends of every exchange: direct peer copies are the default (measured against the alternatives,
+    // profiles/exchange_r02_*: copies 1.701 / NCCL 1.710 / peer stores 1.724 ms per step at two GPUs; 1.73 / 1.80 at eight)
+    const char* xe = getenv("SPH_B200_MULTI_XCHG");          // "copy" (default) | "nccl" | "peer"
+    m->peerStores = xe && strcmp(xe, "peer") == 0;
+    m->copyExchange = repeated || m->peerStores || !(xe && strcmp(xe, "nccl") == 0);     // peer stores need the same peer access
     if (ndev > 1 && !m->copyExchange && !load_nccl(why)) { delete m;  return mfail(nullptr, SPH_ERR_CUDA, "sph_multi_create: %s", why.c_str()); }
     int rc = create_common(m, params, capacityPerSlab);
     if (rc == SPH_OK && ndev > 1 && m->copyExchange) {
@@ -537,7 +549,7 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
             auto mark = [&](int k) { if (m->phaseTiming) cudaEventRecord(r.evPhase[k], s->stream); };
             mark(0);
-            if (m->copyExchange && multi) {
+            if (m->copyExchange && !m->peerStores && multi) {
                 // the neighbours pulled this slab's out buffers on THEIR exchange streams: wait for last step's pulls
                 if (r.hasLower) { MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX1, 0));  MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evX2, 0)); }
                 if (r.hasUpper) { MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evX1, 0));  MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evX2, 0)); }
@@ -551,7 +563,9 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
                                                         b.zLo, b.zHi, b.hasLower, b.hasUpper,
                                                         r.msgDown + kRecFloats, r.msgUp + kRecFloats, capL,
                                                         r.msgDown + (size_t)kRecFloats * (1 + capL), r.msgUp + (size_t)kRecFloats * (1 + capL), capB,
-                                                        reinterpret_cast<uint32_t*>(r.msgDown), reinterpret_cast<uint32_t*>(r.msgUp));
+                                                        reinterpret_cast<uint32_t*>(r.msgDown), reinterpret_cast<uint32_t*>(r.msgUp),
+                                                        m->peerStores && r.hasLower ? m->ranks[r.rank - 1].inAbove : nullptr,
+                                                        m->peerStores && r.hasUpper ? m->ranks[r.rank + 1].inBelow : nullptr);
                 MCU(m, cudaEventRecord(r.evA, s->stream));
             }
             mark(1);
@@ -560,7 +574,7 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
                                           (uint32_t)((b.lowLayers + nz) * yx), s->keyMax, 1);
             mark(2);
         }
-        if (multi)
+        if (multi && !m->peerStores)
             if (int rc = exchange(m, msg_bytes(m), &MultiRank::evA, &MultiRank::msgDown, &MultiRank::msgUp, &MultiRank::inBelow, &MultiRank::inAbove)) return rc;
         // ---- arrivals + ghosts, sort, density, rho,p rows
         for (MultiRank& r : m->ranks) {
@@ -571,8 +585,13 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             const int yx = (int)s->par.gridSize_yx, nz = b.zHi - b.zLo;
             auto mark = [&](int k) { if (m->phaseTiming) cudaEventRecord(r.evPhase[k], s->stream); };
             if (multi) {
-                MCU(m, cudaEventRecord(r.evX1, r.xs));
-                MCU(m, cudaStreamWaitEvent(s->stream, r.evX1, 0));
+                if (m->peerStores) {            // the neighbours' packing kernels wrote this slab's inboxes: wait for THEM
+                    if (r.hasLower) MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evA, 0));
+                    if (r.hasUpper) MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evA, 0));
+                } else {
+                    MCU(m, cudaEventRecord(r.evX1, r.xs));
+                    MCU(m, cudaStreamWaitEvent(s->stream, r.evX1, 0));
+                }
                 mark(3);
                 sph_launch_slab_unpack_hist(L, s->par, r.hasLower ? r.inBelow : nullptr, r.hasUpper ? r.inAbove : nullptr,
                                             r.hasLower ? r.msgDown : nullptr, r.hasUpper ? r.msgUp : nullptr, capL, capB,
@@ -590,12 +609,15 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
             if (s->timing) cudaEventRecord(s->ev[4], s->stream);
             mark(6);
             if (multi) {
-                sph_launch_slab_pack_dp(L, s->posP, s->velD, s->counters, r.dpDown, r.dpUp, capB);
+                // peer stores: the rows go straight into the neighbours' row inboxes
+                float4* down = m->peerStores ? (r.hasLower ? m->ranks[r.rank - 1].dpAbove : r.dpDown) : r.dpDown;
+                float4* up = m->peerStores ? (r.hasUpper ? m->ranks[r.rank + 1].dpBelow : r.dpUp) : r.dpUp;
+                sph_launch_slab_pack_dp(L, s->posP, s->velD, s->counters, down, up, capB);
                 MCU(m, cudaEventRecord(r.evDp, s->stream));
             }
             mark(7);
         }
-        if (multi)
+        if (multi && !m->peerStores)
             if (int rc = exchange(m, dp_bytes(m), &MultiRank::evDp, &MultiRank::dpDown, &MultiRank::dpUp, &MultiRank::dpBelow, &MultiRank::dpAbove)) return rc;
         // ---- force: CTAs without ghost neighbours while the rows travel, then the rest
         for (MultiRank& r : m->ranks) {
@@ -611,10 +633,13 @@ extern "C" int sph_multi_step(sph_multi_t* m, int nsteps)
                                  s->ctaRows, s->vel, 0, r.capacity, 0, -1, dev, part, 2 * (capB / s->cfg.threads + 2));
             };
             if (multi) {
-                MCU(m, cudaEventRecord(r.evX2, r.xs));
+                if (!m->peerStores) MCU(m, cudaEventRecord(r.evX2, r.xs));
                 force(1);
                 mark(8);
-                MCU(m, cudaStreamWaitEvent(s->stream, r.evX2, 0));
+                if (m->peerStores) {
+                    if (r.hasLower) MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank - 1].evDp, 0));
+                    if (r.hasUpper) MCU(m, cudaStreamWaitEvent(s->stream, m->ranks[r.rank + 1].evDp, 0));
+                } else MCU(m, cudaStreamWaitEvent(s->stream, r.evX2, 0));
                 mark(9);
                 sph_launch_slab_unpack_dp(L, r.hasLower ? r.dpBelow : nullptr, r.hasUpper ? r.dpAbove : nullptr, s->counters, s->posP, s->velD, capB);
                 mark(10);

@@ -756,8 +756,11 @@ k_slab_boundary_integrate_pack(const __grid_constant__ SimParams par, const Boun
                                int zLo, int zHi, int hasLower, int hasUpper,
                                SlabRecord* __restrict__ leavDown, SlabRecord* __restrict__ leavUp, int capL,
                                SlabRecord* __restrict__ bndDown, SlabRecord* __restrict__ bndUp, int capB,
-                               uint32_t* __restrict__ headDown, uint32_t* __restrict__ headUp)
+                               uint32_t* __restrict__ headDown, uint32_t* __restrict__ headUp,
+                               SlabRecord* __restrict__ peerDown, SlabRecord* __restrict__ peerUp)
 {
+    // peerDown / peerUp (peer-store exchange): the neighbours' INBOXES, written straight over NVLink -- row 0 is the header
+    // (published by k_slab_publish_headers once the counts are final), leaver rows from 1, boundary rows from 1 + capL
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t g0 = st[SD_FIRST], g1 = st[SD_END], bLo = st[SD_BLO2], bHi = st[SD_BHI2];
     const uint32_t nLo = bLo - g0, nHi = g1 - bHi;
@@ -789,11 +792,22 @@ k_slab_boundary_integrate_pack(const __grid_constant__ SimParams par, const Boun
     const uint32_t sBndDown = warp_append_slot(headDown + 1, copyDown), sBndUp = warp_append_slot(headUp + 1, copyUp);
     if (!(goDown || goUp || copyDown || copyUp)) return;
     SlabRecord r;  r.pos = pOut;  r.vel = vOut;  r.meta = make_uint4(id, 0u, 0u, 0u);
-    if (goDown) { if (sLeavDown < (uint32_t)capL) leavDown[sLeavDown] = r; }
-    else if (goUp) { if (sLeavUp < (uint32_t)capL) leavUp[sLeavUp] = r; }
+    // leavers stay in the local message too: they are this slab's own ghosts on that side (k_slab_unpack_hist)
+    if (goDown) { if (sLeavDown < (uint32_t)capL) { leavDown[sLeavDown] = r;  if (peerDown) peerDown[1 + sLeavDown] = r; } }
+    else if (goUp) { if (sLeavUp < (uint32_t)capL) { leavUp[sLeavUp] = r;  if (peerUp) peerUp[1 + sLeavUp] = r; } }
     if (goDown || goUp) idx[i] = kDeadIndex;
-    if (copyDown && sBndDown < (uint32_t)capB) bndDown[sBndDown] = r;
-    if (copyUp && sBndUp < (uint32_t)capB) bndUp[sBndUp] = r;
+    if (copyDown && sBndDown < (uint32_t)capB) { if (peerDown) peerDown[1 + capL + sBndDown] = r; else bndDown[sBndDown] = r; }
+    if (copyUp && sBndUp < (uint32_t)capB) { if (peerUp) peerUp[1 + capL + sBndUp] = r; else bndUp[sBndUp] = r; }
+}
+
+// peer-store exchange: the final counts of this slab's two messages go into the header rows of the neighbours' inboxes
+__global__ void k_slab_publish_headers(const uint32_t* __restrict__ headDown, const uint32_t* __restrict__ headUp,
+                                       uint32_t* __restrict__ peerDown, uint32_t* __restrict__ peerUp)
+{
+    if (threadIdx.x < 2) {
+        if (peerDown) peerDown[threadIdx.x] = headDown[threadIdx.x];
+        if (peerUp) peerUp[threadIdx.x] = headUp[threadIdx.x];
+    }
 }
 
 // local key of a live particle: global hash minus the slab's offset; anything outside the local table goes to the dummy
@@ -1121,13 +1135,18 @@ void sph_launch_slab_unpack(const SphLaunch& L, const void* inBelow, const void*
 void sph_launch_slab_boundary_integrate_pack(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,
                                              uint32_t* st, int bound, int zLo, int zHi, int hasLower, int hasUpper,
                                              void* leavDown, void* leavUp, int capL, void* bndDown, void* bndUp, int capB,
-                                             uint32_t* headDown, uint32_t* headUp)
+                                             uint32_t* headDown, uint32_t* headUp, void* peerDown, void* peerUp)
 {
     const BoundaryCtx ctx = boundary_ctx(par);
     k_slab_boundary_integrate_pack<<<blocks_for(bound, 256), 256, 0, L.stream>>>(par, ctx, pos, vel, idx, st, zLo, zHi, hasLower, hasUpper,
                                                                                   (SlabRecord*)leavDown, (SlabRecord*)leavUp, capL,
-                                                                                  (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp);
+                                                                                  (SlabRecord*)bndDown, (SlabRecord*)bndUp, capB, headDown, headUp,
+                                                                                  (SlabRecord*)peerDown, (SlabRecord*)peerUp);
     SPH_COUNT(L);
+    if (peerDown || peerUp) {
+        k_slab_publish_headers<<<1, 32, 0, L.stream>>>(headDown, headUp, (uint32_t*)peerDown, (uint32_t*)peerUp);
+        SPH_COUNT(L);
+    }
 }
 
 void sph_launch_slab_interior_hist(const SphLaunch& L, const SimParams& par, float4* pos, float4* vel, uint32_t* idx,

@@ -103,3 +103,22 @@ def test_streaming_kernels_have_no_local_memory(resources):
     for needle in ("k_rank_gather", "k_bucket", "k_scan_apply", "k_scan_reduce", "k_slab_hash_hist"):
         for res in _one(resources, needle):
             assert res["stack"] == 0 and res["local"] == 0, needle
+
+
+def test_warp_collectives_carry_the_scan_and_the_slab_appends(sass):
+    """Warp shuffles / votes / reductions where the step needs a warp-wide answer: the cell-table scan, the largest-cell and
+    key-bound maxima, and the warp-aggregated message appends and dummy-cell counts of the slab kernels."""
+    for needle, ops in (("k_scan_apply", ("SHFL",)), ("k_scan_tiles", ("SHFL",)),
+                        ("k_slab_boundary_integrate_pack", ("VOTE", "SHFL")), ("k_slab_interior_hist", ("VOTE", "SHFL", "REDUX")),
+                        ("k_slab_unpack_hist", ("REDUX",))):
+        for code in _one(sass, needle):
+            text = "\n".join(code)
+            for op in ops:
+                assert op in text, (needle, op)
+
+
+def test_big_cell_rank_kernel_stages_through_shared_memory(sass, resources):
+    (code,) = _one(sass, "k_rank_big_cells")
+    assert any(i.startswith("LDS") for i in code) and any(i.startswith("STS") for i in code)
+    (res,) = _one(resources, "k_rank_big_cells")
+    assert res["shared"] >= 4096 and res["stack"] == 0

@@ -83,6 +83,18 @@ def test_multi_driver_other_pair_variants(monkeypatch, variant):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("slabs", [2, 4])
+def test_multi_driver_peer_store_exchange(monkeypatch, slabs):
+    """SPH_B200_MULTI_XCHG=peer: no exchange copy at all -- the packing kernels store leavers, boundary copies and rho,p rows
+    straight into the neighbours' inboxes and the receivers wait for the senders' kernels.  Same results, with a re-cut."""
+    monkeypatch.setenv("SPH_B200_MULTI_XCHG", "peer")
+    got, owned0, info = multi_run("wave tank 256k" if slabs == 4 else "mini waves", 10, slabs, recut_every=4)
+    ref = single_gpu_run("wave tank 256k" if slabs == 4 else "mini waves", 10)
+    for a, b, what in zip(got, ref, ("positions", "velocities", "densities")):
+        assert np.array_equal(a, b), f"{what} differ"
+    assert info["owned"] != owned0 and info["bytes_sent"] == 0
+
+
 def test_multi_driver_recut_keeps_the_results(monkeypatch):
     """Re-cutting the slabs every three steps changes who owns what, never the result."""
     got, _, info = multi_run("mini waves", 10, 3, recut_every=3)
@@ -120,6 +132,30 @@ def free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def test_multi_driver_one_process_two_gpus_nccl_and_copies(monkeypatch):
+    """One process driving two DIFFERENT GPUs: ncclCommInitAll + grouped ncclSend/ncclRecv, and the default peer copies."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ref = single_gpu_run("wave tank 256k", 8)
+    for mode in ("nccl", "copy", "peer"):
+        monkeypatch.setenv("SPH_B200_MULTI_XCHG", mode)
+        s = host.CSph(device=-1)
+        s.select_scene("wave tank 256k")
+        pos, vel = s.host_arrays()
+        m = lib.MultiSystem(s.params, capacity_per_slab=s.n, devices=[0, 1])
+        m.set_state(pos, stir(vel))
+        for _ in range(8):
+            s.UpdateEmitter()
+            m.set_params(s.params)
+            m.step(1)
+        p, v, d, _, written = m.get_state(density=True)
+        sent = m.info()["bytes_sent"]
+        m.close()
+        assert written == s.n and (sent > 0) == (mode != "peer")
+        assert np.array_equal(p, ref[0]) and np.array_equal(v, ref[1]) and np.array_equal(d, ref[2]), mode
 
 
 def test_multi_driver_nccl_two_processes(tmp_path):
