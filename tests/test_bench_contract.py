@@ -39,3 +39,27 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_under_torchrun_only_rank_zero_prints():
     assert len(_run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")) == 1
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2") == []
+
+
+def test_state_checksum_is_order_independent_and_bit_sensitive():
+    """bench.py's full-size multi-GPU parity compares an order-independent checksum of (id, pos, vel, rho): equal for any
+    distribution of the same particles over slabs, different as soon as one bit of one particle differs."""
+    import numpy as np
+    sys.path.insert(0, str(ROOT))
+    import bench
+    rng = np.random.default_rng(3)
+    n = 5000
+    ids = np.arange(n, dtype=np.uint32)
+    pos, vel = rng.random((n, 4), np.float32), rng.random((n, 4), np.float32)
+    dens = rng.random(n, np.float32)
+    whole = bench.state_checksum(ids, pos, vel, dens)
+    perm = rng.permutation(n)
+    parts = np.array_split(perm, 3)
+    split = sum(bench.state_checksum(ids[p], pos[p], vel[p], dens[p]) for p in parts) & 0xFFFFFFFFFFFFFFFF
+    assert split == whole
+    v2 = vel.copy()
+    v2.view(np.uint32)[1234, 2] ^= 1                      # one ulp of one component of one particle
+    assert bench.state_checksum(ids, pos, v2, dens) != whole
+    swapped = ids.copy()
+    swapped[[10, 11]] = swapped[[11, 10]]                 # two particles exchanging their states
+    assert bench.state_checksum(swapped, pos, vel, dens) != whole
