@@ -715,7 +715,10 @@ def main():
         s.close()
         out["cpu_baseline"], out["parity_check"] = cpu_baseline(out["config"]["workload"])
         if args.workload is None:
-            out["scaling_base"] = scaling_base(min(args.steps, 30), 5)
+            try:
+                out["scaling_base"] = scaling_base(min(args.steps, 30), 5)
+            except Exception as e:                           # noqa: BLE001 -- an extra, never worth losing the line for
+                out["scaling_base"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(out), flush=True)
 
 
