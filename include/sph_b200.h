@@ -102,6 +102,11 @@ int sph_sync(sph_t* s);                                      /* threadSync, Syst
 int sph_set_array(sph_t* s, int which /*SPH_POS|SPH_VEL*/, const float* xyzw, int start, int count);
 /* cSPH::getArray (SPH_Util.cpp:44-56) generalised to a range and to the scalar arrays.  Blocking. */
 int sph_get_array(sph_t* s, int which, float* out, int start, int count);
+/* Whole state out and whole new state in with ONE call: semantics of sph_get_array(SPH_POS), sph_get_array(SPH_VEL) followed
+ * by sph_set_array(SPH_POS), sph_set_array(SPH_VEL) over the full range, but the device->host copies of the current state
+ * overlap the host->device copies of the new one (PCIe is full duplex).  Blocking; use pinned host memory.  No counterpart
+ * in the reference (cSPH::getArray / setArray are one blocking copy each, SPH_Util.cpp:44-71). */
+int sph_exchange_arrays(sph_t* s, float* outPos, float* outVel, const float* inPos, const float* inVel);
 /* Device-resident variants (no host copy): src/dst are device pointers on the handle's device. */
 int sph_set_array_device(sph_t* s, int which, const float* d_xyzw, int start, int count);
 int sph_get_array_device(sph_t* s, int which, float* d_out, int start, int count);

@@ -135,6 +135,9 @@ public:
 
     float4* getArray(bool pos);                 // NB inverted flag as in the reference: false = positions, true = velocities
     void setArray(bool pos, const float4* data, int start, int count);
+    // getArray(false), getArray(true) into the caller's buffers, then setArray of both from the caller's new state, as one
+    // call whose downloads overlap its uploads (sph_exchange_arrays; pinned buffers make the overlap real).  0 on success.
+    int exchangeArrays(float4* outPos, float4* outVel, const float4* inPos, const float4* inVel);
     uint getPosBuffer() const { return posVbo[curPosRead]; }    // GL id of the position buffer (SPH.h:29); 0 when headless
     const float4* getPosDevice() const;         // device pointer of the live positions (sorted order), for headless callers
     // Hands the renderer's GL buffers to the solver (the reference creates them itself in _InitMem,

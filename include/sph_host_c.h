@@ -54,6 +54,8 @@ int  sphh_update(sphh_t* h, int nsteps);
 void sphh_mark_changed(sphh_t* h);                                  /* ParamBase::bChangedAny = true */
 
 int  sphh_get_array(sphh_t* h, int velocities, float* out);
+/* cSPH::exchangeArrays: current positions + velocities out, new ones in, downloads overlapping uploads */
+int  sphh_exchange_arrays(sphh_t* h, float* outPos, float* outVel, const float* inPos, const float* inVel);
 void sphh_set_array(sphh_t* h, int velocities, const float* data, int start, int count);
 sph_t* sphh_solver(sphh_t* h);
 int  sphh_save_state(sphh_t* h, const char* path);                  /* checkpoint: params, pos, vel, ring counters */

@@ -24,6 +24,10 @@ void sphh_destroy(sphh_t* h) { delete reinterpret_cast<cSPH*>(h); }
 static cSPH* S(sphh_t* h) { return reinterpret_cast<cSPH*>(h); }
 
 sph_multi_t* sphh_multi_solver(sphh_t* h) { return S(h)->multiSolver(); }
+int sphh_exchange_arrays(sphh_t* h, float* outPos, float* outVel, const float* inPos, const float* inVel)
+{
+    return S(h)->exchangeArrays((float4*)outPos, (float4*)outVel, (const float4*)inPos, (const float4*)inVel);
+}
 int sphh_num_scenes(sphh_t* h) { return (int)S(h)->scenes.size(); }
 int sphh_cur_scene(sphh_t* h) { return S(h)->curScene; }
 const char* sphh_last_error(sphh_t* h) { return S(h)->lastError(); }

@@ -462,6 +462,26 @@ void cSPH::setArray(bool pos, const float4* data, int start, int count)
     if (data != mirror + start) memcpy(mirror + start, data, (size_t)count * sizeof(float4));
 }
 
+int cSPH::exchangeArrays(float4* outPos, float4* outVel, const float4* inPos, const float4* inVel)
+{
+    if (!bInitialized) return SPH_ERR_STATE;
+    const size_t bytes = (size_t)scn.params.numParticles * sizeof(float4);
+    if (msys || !sys) {                 // several GPUs (or no solver): the plain accessors, one after the other
+        float4* p = getArray(false);
+        if (p != outPos) memcpy(outPos, p, bytes);
+        float4* v = getArray(true);
+        if (v != outVel) memcpy(outVel, v, bytes);
+        setArray(false, inPos, 0, (int)scn.params.numParticles);
+        setArray(true, inVel, 0, (int)scn.params.numParticles);
+        return SPH_OK;
+    }
+    int rc = sph_exchange_arrays(sys, (float*)outPos, (float*)outVel, (const float*)inPos, (const float*)inVel);
+    if (rc != SPH_OK) { err = sph_last_error(sys);  return rc; }
+    if (inPos != hPos) memcpy(hPos, inPos, bytes);          // the mirrors follow what the device now holds
+    if (inVel != hVel) memcpy(hVel, inVel, bytes);
+    return SPH_OK;
+}
+
 const float4* cSPH::getPosDevice() const
 {
     const float* d = nullptr;

@@ -48,6 +48,9 @@ extern "C" int sph_destroy(sph_t* s)
     void* bufs[] = {s->pos[0], s->pos[1], s->vel, s->velS, s->posP, s->velD, s->io, s->idx[0], s->idx[1], s->keyU,
                     s->rankU, s->keyS, s->counts, s->pairT, s->nlist, s->ncount, s->cellCount, s->cellStart, s->tileSums, s->maxCount, s->ctaRows, s->counters, s->keyMax, s->clr, s->dye};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (float4* b : s->xio) if (b) cudaFree(b);
+    if (s->ioStream) cudaStreamDestroy(s->ioStream);
+    if (s->evIn) cudaEventDestroy(s->evIn);
     for (auto& g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& r : s->glRes) if (r) cudaGraphicsUnregisterResource(r);
     if (s->hostInts) cudaFreeHost(s->hostInts);
@@ -441,6 +444,43 @@ extern "C" int sph_get_array(sph_t* s, int which, float* out, int start, int cou
     if (rc) return rc;
     size_t elem = (which == SPH_POS || which == SPH_VEL || which == SPH_COLOR) ? sizeof(float4) : sizeof(float);
     CU_TRY(s, cudaMemcpyAsync(out, s->io, (size_t)count * elem, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return SPH_OK;
+}
+
+// The whole state out to the host and a whole new state in, in one call: the device->host copies of the CURRENT positions and
+// velocities run while the host->device copies of the NEW ones do (PCIe is full duplex; a get followed by a set would
+// serialise them).  Semantics = sph_get_array(POS), sph_get_array(VEL), then sph_set_array(POS), sph_set_array(VEL), all over
+// the full range, original particle order; returns when all four copies are done.  Pinned host memory on both sides is what
+// makes the overlap real.
+extern "C" int sph_exchange_arrays(sph_t* s, float* outPos, float* outVel, const float* inPos, const float* inVel)
+{
+    if (!s || !outPos || !outVel || !inPos || !inVel) return SPH_ERR_ARG;
+    if (s->slab.on) return fail(s, SPH_ERR_STATE, "sph_exchange_arrays: handle is in slab mode");
+    CU_TRY(s, cudaSetDevice(s->device));
+    const int n = (int)s->par.numParticles;
+    const size_t bytes = (size_t)n * sizeof(float4);
+    if (!s->ioStream) {
+        for (float4*& b : s->xio) CU_TRY(s, cudaMalloc((void**)&b, (size_t)s->nAlloc * sizeof(float4)));
+        CU_TRY(s, cudaStreamCreateWithFlags(&s->ioStream, cudaStreamNonBlocking));
+        CU_TRY(s, cudaEventCreateWithFlags(&s->evIn, cudaEventDisableTiming));
+    }
+    SphLaunch L = launcher(s);
+    float4 *outP = s->io, *outV = s->xio[0], *inP = s->xio[1], *inV = s->xio[2];
+    // in: host -> staging on the second stream, at once
+    CU_TRY(s, cudaMemcpyAsync(inP, inPos, bytes, cudaMemcpyHostToDevice, s->ioStream));
+    CU_TRY(s, cudaMemcpyAsync(inV, inVel, bytes, cudaMemcpyHostToDevice, s->ioStream));
+    CU_TRY(s, cudaEventRecord(s->evIn, s->ioStream));
+    // out: current state into original order, then to the host on the solver stream
+    sph_launch_unpermute4(L, s->pos[s->cur], s->idx[s->cur], outP, 0, n, n);
+    sph_launch_unpermute4(L, s->vel, s->idx[s->cur], outV, 0, n, n);
+    CU_TRY(s, cudaMemcpyAsync(outPos, outP, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(outVel, outV, bytes, cudaMemcpyDeviceToHost, s->stream));
+    // the new state replaces the old one once both have been read / have arrived
+    CU_TRY(s, cudaStreamWaitEvent(s->stream, s->evIn, 0));
+    sph_launch_permute4(L, s->pos[s->cur], s->idx[s->cur], inP, 0, n, n);
+    sph_launch_permute4(L, s->vel, s->idx[s->cur], inV, 0, n, n);
+    CU_TRY(s, cudaGetLastError());
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     return SPH_OK;
 }

@@ -54,6 +54,10 @@ struct sph_system {
     uint32_t* counters = nullptr;           // device: 4 append counters
     uint32_t* keyMax = nullptr;             // device: slab scan bound (sph_device.cuh kKeyMaxSlots)
     uint32_t* hostInts = nullptr;           // pinned: read-back of counters / cell-table entries
+    // sph_exchange_arrays: three more staging buffers and a second stream, allocated on first use
+    float4* xio[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t ioStream = nullptr;
+    cudaEvent_t evIn = nullptr;
 
     bool timing = false;
     cudaEvent_t ev[SPH_STAGE_COUNT + 1] = {};

@@ -25,6 +25,7 @@ HOST_ABI_SYMBOLS = (
     "sphh_mark_changed", "sphh_get_array", "sphh_set_array", "sphh_solver", "sphh_load_options",
     "sphh_save_state", "sphh_load_state", "sphh_set_targets", "sphh_set_emitter", "sphh_cnt_rain", "sphh_changed_flag",
     "sphh_register_gl", "sphh_pos_buffer", "sphh_timer_fps", "sphh_create_multi", "sphh_multi_solver",
+    "sphh_exchange_arrays",
 )
 
 EXTRA_FIELDS = ("initMin", "initMax", "initType", "initLast", "spacing", "fCellSize", "dropR", "rain", "rVel", "r2Vel",
@@ -42,6 +43,7 @@ def _bind():
     L.sphh_create.restype = vp;            L.sphh_create.argtypes = [cs, ci]
     L.sphh_create_multi.restype = vp;      L.sphh_create_multi.argtypes = [cs, C.POINTER(ci), ci]
     L.sphh_multi_solver.restype = vp;      L.sphh_multi_solver.argtypes = [vp]
+    L.sphh_exchange_arrays.argtypes = [vp, vp, vp, vp, vp]
     L.sphh_destroy.argtypes = [vp]
     L.sphh_last_error.restype = cs;        L.sphh_last_error.argtypes = [vp]
     L.sphh_num_scenes.argtypes = [vp];     L.sphh_cur_scene.argtypes = [vp]
@@ -262,6 +264,14 @@ class CSph:
     def setArray(self, pos: bool, data: np.ndarray, start: int = 0):
         data = np.ascontiguousarray(data, np.float32).reshape(-1, 4)
         self.L.sphh_set_array(self.h, int(pos), _p(data), start, data.shape[0])
+
+    def exchangeArrays(self, out_pos, out_vel, in_pos, in_vel):
+        """cSPH::exchangeArrays on raw host pointers (ints) or numpy arrays: current state out, new state in, one call."""
+        def ptr(a):
+            return C.c_void_p(a) if isinstance(a, int) else _p(a)
+        rc = self.L.sphh_exchange_arrays(self.h, ptr(out_pos), ptr(out_vel), ptr(in_pos), ptr(in_vel))
+        if rc != 0:
+            raise SphError(f"cSPH::exchangeArrays failed ({rc}): {self.last_error()}")
 
     def SaveState(self, path):
         if self.L.sphh_save_state(self.h, str(path).encode()) != 0:

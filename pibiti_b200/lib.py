@@ -79,7 +79,7 @@ STAGE_NAMES = ("integrate_hash", "sort", "reorder", "density", "force")
 # every symbol include/sph_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "sph_create", "sph_destroy", "sph_set_params", "sph_get_params", "sph_reset_state", "sph_set_visual", "sph_set_dye", "sph_step", "sph_sync",
-    "sph_set_array", "sph_get_array", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
+    "sph_set_array", "sph_get_array", "sph_exchange_arrays", "sph_set_array_device", "sph_get_array_device", "sph_device_buffers",
     "sph_debug_dump", "sph_get_timings", "sph_kernel_launch_count", "sph_cuda_stream", "sph_last_error",
     "sph_version", "sph_pair_variant", "sph_gl_register", "sph_gl_update",
     "sph_slab_configure", "sph_slab_set_owned", "sph_slab_get_owned", "sph_slab_integrate", "sph_slab_pack", "sph_slab_integrate_pack",
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     lib.sph_sync.argtypes = [vp]
     lib.sph_set_array.argtypes = [vp, ci, vp, ci, ci]
     lib.sph_get_array.argtypes = [vp, ci, vp, ci, ci]
+    lib.sph_exchange_arrays.argtypes = [vp, vp, vp, vp, vp]
     lib.sph_set_array_device.argtypes = [vp, ci, vp, ci, ci]
     lib.sph_get_array_device.argtypes = [vp, ci, vp, ci, ci]
     lib.sph_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]

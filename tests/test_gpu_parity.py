@@ -705,3 +705,38 @@ def test_pile_up_cells_take_the_big_cell_rank_path(oracle_any, monkeypatch, vari
     vg, vo = g.get_array(lib.SPH_VEL), o.get_array(1)
     assert np.all(np.abs(vg - vo) <= REL * max(float(np.abs(vo[:, :3]).max()), 1e-3))
     o.close()
+
+
+def test_exchange_arrays_equals_get_then_set(oracle_any):
+    """cSPH::exchangeArrays (downloads overlapping uploads) == getArray(pos), getArray(vel), setArray(pos), setArray(vel):
+    same data out, same trajectory afterwards -- on a stepped (sorted) state, with pinned and with pageable buffers."""
+    import torch
+    def run(use_exchange, pinned):
+        s = host.CSph(device=0)
+        s.select_scene("mini waves")
+        s.Update(3)
+        n = s.n
+        rng = np.random.Generator(np.random.PCG64(9))
+        new_pos = s.getArray(False).copy()
+        new_pos[:, :3] += rng.uniform(-1e-4, 1e-4, (n, 3)).astype(np.float32)
+        new_vel = (s.getArray(True) * np.float32(0.5)).astype(np.float32)
+        mk = (lambda a: torch.from_numpy(a.copy()).pin_memory()) if pinned else (lambda a: torch.from_numpy(a.copy()))
+        ip, iv = mk(new_pos), mk(new_vel)
+        op, ov = mk(np.zeros((n, 4), np.float32)), mk(np.zeros((n, 4), np.float32))
+        if use_exchange:
+            s.exchangeArrays(op.data_ptr(), ov.data_ptr(), ip.data_ptr(), iv.data_ptr())
+            outs = op.numpy().copy(), ov.numpy().copy()
+        else:
+            outs = s.getArray(False).copy(), s.getArray(True).copy()
+            s.setArray(False, new_pos)
+            s.setArray(True, new_vel)
+        assert np.array_equal(s.getArray(False), new_pos) and np.array_equal(s.getArray(True), new_vel)
+        s.Update(2)
+        res = outs + (s.getArray(False).copy(), s.getArray(True).copy())
+        s.close()
+        return res
+    ref = run(False, False)
+    for pinned in (True, False):
+        got = run(True, pinned)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
