@@ -469,16 +469,21 @@ def run_ours_multi(args) -> dict | None:
 
     # end to end with HOST buffers: every step uploads this rank's owned records from pinned memory and reads them back
     e2e_steps = max(3, min(args.steps, 5))
+    # inputs: the records fetched above, uploaded again every step; outputs: each step's result, read one call later by the
+    # duplex accessor (download overlapping the next upload), the last one by a plain fetch before the clock stops
+    out_rec = torch.empty((m.capacity, 12), dtype=torch.float32, pin_memory=True)
     dist.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(e2e_steps):
-        m.put_owned(0, host_rec.data_ptr(), cnt)
+        got = m.exchange_owned(0, out_rec.data_ptr(), m.capacity, host_rec.data_ptr(), cnt)
         h2d += cnt * 48
+        d2h += got * 48
         one_step()
-        cnt = m.fetch_owned(0, host_rec.data_ptr(), m.capacity)
-        d2h += cnt * 48
+    got = m.fetch_owned(0, out_rec.data_ptr(), m.capacity)
+    d2h += got * 48
     m.sync()
+    host_rec, cnt = out_rec, got
     dist.barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
@@ -506,7 +511,8 @@ def run_ours_multi(args) -> dict | None:
         "clocks": clocks,
         "e2e": {"value": n * e2e_steps / float(e2e_s.item()), "unit": UNIT,
                 "h2d_bytes_per_step": int(io[0].item()) // e2e_steps, "d2h_bytes_per_step": int(io[1].item()) // e2e_steps,
-                "steps": e2e_steps, "api": "per rank: sph_multi_put_owned (pinned host -> device), sph_multi_step, sph_multi_fetch_owned"},
+                "steps": e2e_steps, "api": "per rank: sph_multi_exchange_owned (previous result out, this step's inputs in, download overlapping upload; "
+                       "pinned host memory), sph_multi_step; the last result by sph_multi_fetch_owned inside the timed region"},
         "gpu_launches": int(launches),
         "halo_bytes_per_step_rank0": info1["bytes_sent"] // max(total_steps, 1),
         "phase_ms_last_step_by_rank": phases,

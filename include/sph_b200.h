@@ -211,6 +211,9 @@ int sph_multi_get_state(sph_multi_t* m, float* pos, float* vel, float* dens, flo
  * that lie in the slab's layers (what fetch returned, possibly modified). */
 int sph_multi_fetch_owned(sph_multi_t* m, int local, float* hostRecords, int capacityRecords, int* count);
 int sph_multi_put_owned(sph_multi_t* m, int local, const float* hostRecords, int count);
+/* fetch + put as one blocking call whose download overlaps its upload (full-duplex link; use pinned memory) */
+int sph_multi_exchange_owned(sph_multi_t* m, int local, float* outRecords, int outCapacity, int* outCount,
+                             const float* inRecords, int inCount);
 /* phase profile of the last step of a local slab, ms on its solver stream: {edge integrate + pack, interior integrate +
  * histogram, wait for the particle exchange, unpack arrivals, scan + bucket + gather, density, pack rho/p rows, interior
  * force, wait for the rho/p exchange, unpack rho/p rows, boundary force}; enable it first */

@@ -89,6 +89,8 @@ struct MultiRank {
     float4 *dpDown = nullptr, *dpUp = nullptr, *dpBelow = nullptr, *dpAbove = nullptr;       // rho,p rows
     cudaEvent_t evA = nullptr, evX1 = nullptr, evDp = nullptr, evX2 = nullptr;
     cudaEvent_t evPhase[12] = {};               // phase profile of the last step (sph_multi_phase_ms)
+    float* xstage = nullptr;                    // sph_multi_exchange_owned: staging of the incoming records (lazy)
+    cudaEvent_t evXin = nullptr;
     uint32_t* hostSt = nullptr;                 // pinned copy of the device words
     int owned = 0;                              // as of the last sph_multi_sync / set_state
 };
@@ -386,6 +388,8 @@ extern "C" int sph_multi_destroy(sph_multi_t* m)
         cudaEvent_t evs[] = {r.evA, r.evX1, r.evDp, r.evX2};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : r.evPhase) if (e) cudaEventDestroy(e);
+        if (r.xstage) cudaFree(r.xstage);
+        if (r.evXin) cudaEventDestroy(r.evXin);
         if (r.xs) cudaStreamDestroy(r.xs);
         if (r.hostSt) cudaFreeHost(r.hostSt);
         if (r.s) sph_destroy(r.s);
@@ -883,3 +887,36 @@ extern "C" int sph_multi_set_recut_interval(sph_multi_t* m, int steps)
 }
 
 extern "C" int sph_multi_recut_count(sph_multi_t* m) { return m ? m->recuts : 0; }
+
+// fetch_owned and put_owned as ONE blocking call: the download of the slab's current owned records overlaps the upload of the
+// new ones (the link is full duplex; a fetch followed by a put would serialise them).  The new records must lie in the slab's
+// layers, as for sph_multi_put_owned.
+extern "C" int sph_multi_exchange_owned(sph_multi_t* m, int local, float* outRecords, int outCapacity, int* outCount,
+                                        const float* inRecords, int inCount)
+{
+    if (!m || local < 0 || local >= (int)m->ranks.size() || !outRecords || !outCount || !inRecords || inCount < 0) return SPH_ERR_ARG;
+    if (!m->haveState) return mfail(m, SPH_ERR_STATE, "sph_multi_exchange_owned: call sph_multi_set_state first (it fixes the cuts)");
+    MultiRank& r = m->ranks[local];
+    if (inCount > r.capacity) return mfail(m, SPH_ERR_ARG, "sph_multi_exchange_owned: %d records exceed the slab capacity %d", inCount, r.capacity);
+    if (int rc = sync_rank(m, r)) return rc;
+    sph_system* s = r.s;
+    const int first = (int)r.hostSt[SD_FIRST], n = (int)(r.hostSt[SD_END] - r.hostSt[SD_FIRST]);
+    *outCount = n;
+    if (n > outCapacity) return mfail(m, SPH_ERR_ARG, "sph_multi_exchange_owned: %d records, room for %d", n, outCapacity);
+    if (!r.xstage) {
+        MCU(m, cudaMalloc((void**)&r.xstage, (size_t)r.capacity * kRecFloats * sizeof(float)));
+        MCU(m, cudaEventCreateWithFlags(&r.evXin, cudaEventDisableTiming));
+    }
+    // in: host -> staging on the exchange stream, at once
+    MCU(m, cudaMemcpyAsync(r.xstage, inRecords, (size_t)inCount * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, r.xs));
+    MCU(m, cudaEventRecord(r.evXin, r.xs));
+    // out: current owned records -> staging -> host on the solver stream
+    if (n > 0) {
+        float* stage = reinterpret_cast<float*>(s->nlist);
+        sph_launch_slab_export(sph_launcher(s), s->pos[s->cur], s->vel, s->idx[s->cur], s->stepped ? s->posP : nullptr,
+                               s->stepped ? s->velD : nullptr, first, n, stage);
+        MCU(m, cudaMemcpyAsync(outRecords, stage, (size_t)n * kRecFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    MCU(m, cudaStreamWaitEvent(s->stream, r.evXin, 0));
+    return load_slab(m, r, r.xstage, inCount);          // ends with a stream synchronise: both directions are done
+}

@@ -88,7 +88,7 @@ ABI_SYMBOLS = (
     "sph_multi_unique_id", "sph_multi_create", "sph_multi_create_rank", "sph_multi_destroy", "sph_multi_last_error",
     "sph_multi_set_params", "sph_multi_set_state", "sph_multi_step", "sph_multi_sync", "sph_multi_get_state",
     "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info", "sph_multi_fetch_owned", "sph_multi_put_owned",
-    "sph_multi_phase_ms", "sph_multi_recut", "sph_multi_set_recut_interval", "sph_multi_recut_count",
+    "sph_multi_phase_ms", "sph_multi_exchange_owned", "sph_multi_recut", "sph_multi_set_recut_interval", "sph_multi_recut_count",
 )
 
 
@@ -165,6 +165,7 @@ def load() -> C.CDLL:
     lib.sph_multi_get_state.argtypes = [vp, vp, vp, vp, vp, ci, ip]
     lib.sph_multi_fetch_owned.argtypes = [vp, ci, vp, ci, ip]
     lib.sph_multi_put_owned.argtypes = [vp, ci, vp, ci]
+    lib.sph_multi_exchange_owned.argtypes = [vp, ci, vp, ci, ip, vp, ci]
     lib.sph_multi_phase_ms.argtypes = [vp, ci, ci, vp]
     lib.sph_multi_recut.argtypes = [vp]
     lib.sph_multi_set_recut_interval.argtypes = [vp, ci]
@@ -372,6 +373,13 @@ class MultiSystem:
         """Owned records of a local slab into host memory at `host_ptr` (e.g. a pinned torch tensor); returns the count."""
         c = C.c_int(0)
         self._check(self.lib.sph_multi_fetch_owned(self.h, local, C.c_void_p(host_ptr), capacity_records, C.byref(c)), "sph_multi_fetch_owned")
+        return c.value
+
+    def exchange_owned(self, local: int, out_ptr: int, out_capacity: int, in_ptr: int, in_count: int) -> int:
+        """fetch_owned + put_owned as one call whose download overlaps its upload; returns the number of records written out."""
+        c = C.c_int(0)
+        self._check(self.lib.sph_multi_exchange_owned(self.h, local, C.c_void_p(out_ptr), out_capacity, C.byref(c),
+                                                      C.c_void_p(in_ptr), in_count), "sph_multi_exchange_owned")
         return c.value
 
     def put_owned(self, local: int, host_ptr: int, count: int):

@@ -218,7 +218,12 @@ def test_fetch_put_owned_round_trip_is_transparent():
                 assert 0 < cnt < s.n
                 ids = buf.numpy()[:cnt, 8].copy().view(np.uint32)
                 assert len(np.unique(ids)) == cnt
-                m.put_owned(local, buf.data_ptr(), cnt)
+                if k == 1:
+                    m.put_owned(local, buf.data_ptr(), cnt)
+                else:                   # the duplex form: what comes out is what went in
+                    out = torch.empty((s.n, 12), dtype=torch.float32, pin_memory=True)
+                    got = m.exchange_owned(local, out.data_ptr(), s.n, buf.data_ptr(), cnt)
+                    assert got == cnt and np.array_equal(out.numpy()[:cnt], buf.numpy()[:cnt])
     p, v, written = m.get_state()
     m.close()
     ref = single_gpu_run("mini waves", 6)
