@@ -36,6 +36,23 @@ CUDA_UNITS = {
 HOST_UNITS = sorted(p.name for p in (CSRC / "host").glob("*.cpp")) if (CSRC / "host").is_dir() else []
 
 
+def _nccl_include() -> list[str]:
+    """nccl.h for sph_multi.cu (types only; the library is dlopen'ed at run time): the system header, else the copy that ships
+    with the nvidia-nccl wheel PyTorch depends on."""
+    if os.path.exists("/usr/include/nccl.h"):
+        return []
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            inc = Path(loc) / "include"
+            if (inc / "nccl.h").exists():
+                return ["-I", str(inc)]
+    except Exception:
+        pass
+    return []
+
+
 def _nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
@@ -68,7 +85,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     for unit, extra in CUDA_UNITS.items():
         src, obj = CSRC / unit, OBJ / (unit + ".o")
         if force or _newer(obj, [src] + headers):
-            cmd = [nvcc] + ARCH + NVCC_COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(src), "-o", str(obj)]
+            cmd = [nvcc] + ARCH + NVCC_COMMON + _nccl_include() + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(src), "-o", str(obj)]
             _run(cmd)
         objs.append(obj)
     for unit in HOST_UNITS:
