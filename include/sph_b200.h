@@ -222,6 +222,8 @@ int sph_multi_phase_ms(sph_multi_t* m, int local, int enable, float* out11);
  * t = 0 only): the slabs synchronise, particles move to their new owners, every slab re-sorts.  Results do not depend on
  * the cuts.  sph_multi_set_recut_interval(m, M) makes sph_multi_step do it every M steps (0 = never). */
 int sph_multi_recut(sph_multi_t* m);
+/* the planner alone (host only): cuts[world+1] from a z-layer histogram, every slab at least two layers */
+int sph_multi_plan_cuts(const long long* layerHistogram, int gridZ, int world, int* cuts);
 int sph_multi_set_recut_interval(sph_multi_t* m, int steps);
 int sph_multi_recut_count(sph_multi_t* m);
 int sph_multi_local_slabs(sph_multi_t* m);

@@ -920,3 +920,15 @@ extern "C" int sph_multi_exchange_owned(sph_multi_t* m, int local, float* outRec
     MCU(m, cudaStreamWaitEvent(s->stream, r.evXin, 0));
     return load_slab(m, r, r.xstage, inCount);          // ends with a stream synchronise: both directions are done
 }
+
+// The cut planner on its own (no GPU needed): layer boundaries that give every slab about the same particle count, at least
+// two layers each, from a z-layer histogram.  What sph_multi_set_state and sph_multi_recut use.
+extern "C" int sph_multi_plan_cuts(const long long* layerHistogram, int gridZ, int world, int* cuts)
+{
+    if (!layerHistogram || !cuts || gridZ < 1 || world < 1) return SPH_ERR_ARG;
+    std::vector<long long> hist(layerHistogram, layerHistogram + gridZ);
+    std::vector<int> c;
+    if (!cut_layers(hist, world, 2, c)) return mfail(nullptr, SPH_ERR_ARG, "sph_multi_plan_cuts: %d z layers are too few for %d slabs", gridZ, world);
+    for (int k = 0; k <= world; k++) cuts[k] = c[k];
+    return SPH_OK;
+}

@@ -89,6 +89,7 @@ ABI_SYMBOLS = (
     "sph_multi_set_params", "sph_multi_set_state", "sph_multi_step", "sph_multi_sync", "sph_multi_get_state",
     "sph_multi_local_slabs", "sph_multi_handle", "sph_multi_stream", "sph_multi_info", "sph_multi_fetch_owned", "sph_multi_put_owned",
     "sph_multi_phase_ms", "sph_multi_exchange_owned", "sph_multi_recut", "sph_multi_set_recut_interval", "sph_multi_recut_count",
+    "sph_multi_plan_cuts",
 )
 
 
@@ -168,6 +169,7 @@ def load() -> C.CDLL:
     lib.sph_multi_exchange_owned.argtypes = [vp, ci, vp, ci, ip, vp, ci]
     lib.sph_multi_phase_ms.argtypes = [vp, ci, ci, vp]
     lib.sph_multi_recut.argtypes = [vp]
+    lib.sph_multi_plan_cuts.argtypes = [vp, ci, ci, ip]
     lib.sph_multi_set_recut_interval.argtypes = [vp, ci]
     lib.sph_multi_recut_count.argtypes = [vp]
     lib.sph_multi_local_slabs.argtypes = [vp]

@@ -172,3 +172,25 @@ def test_gpu_two_process_gloo_slabs_equal_single_gpu(tmp_path):
     steps = 6
     got = run_workers("gpu", "mini waves", steps, tmp_path)
     check_records(got["rec"], single_gpu_run("mini waves", steps))
+
+
+def test_cpp_cut_planner_matches_the_protocol_model():
+    """The multi-GPU driver's cut planner (sph_multi_plan_cuts, C++) against slab.cut_layers (the Python model the gloo tests
+    run on): same boundaries on random layer histograms, thin grids refused by both."""
+    import ctypes as C
+    L = lib.load()
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        gz = int(rng.integers(4, 400))
+        ranks = int(rng.integers(1, 9))
+        n = int(rng.integers(1, 200000))
+        zc = np.minimum((rng.random(n) ** rng.uniform(0.3, 3.0) * gz).astype(np.int64), gz - 1)
+        hist = np.bincount(zc, minlength=gz).astype(np.int64)
+        cuts = (C.c_int * (ranks + 1))()
+        rc = L.sph_multi_plan_cuts(hist.ctypes.data_as(C.c_void_p), gz, ranks, cuts)
+        try:
+            want = slab.cut_layers(zc, gz, ranks)
+        except lib.SphError:
+            assert rc != 0, (gz, ranks)
+            continue
+        assert rc == 0 and list(cuts) == want, (gz, ranks, list(cuts), want)
