@@ -22,7 +22,7 @@
 #include <stdint.h>
 #include "sph_params.h"
 
-#define SPH_SCAN_TILE 4096          // cells per scan block (256 threads x 16)
+#define SPH_SCAN_TILE 4096          // cells per scan block (256 threads x 4 chunks x 4 cells)
 // slab mode: per-block maxima of the live keys land in kKeyMaxSlots words; word [kKeyMaxSlots] is the scan bound
 static const int kKeyMaxSlots = 64;
 

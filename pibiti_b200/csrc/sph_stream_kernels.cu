@@ -273,20 +273,25 @@ __device__ __forceinline__ bool scan_tile_skipped(const uint32_t* __restrict__ b
     return (uint32_t)blockIdx.x * SPH_SCAN_TILE >= __ldg(boundCells) && blockIdx.x != gridDim.x - 1;
 }
 
+// A tile is four chunks of 1024 cells; thread t owns cells [4t, 4t+4) of every chunk, so that a warp reads and writes 512
+// contiguous bytes per instruction (sixteen consecutive cells per thread, the round-1 layout, made every 128-bit access of a
+// warp straddle sixteen lines: the scan ran at a third of the HBM rate).
 __global__ void __launch_bounds__(256)
 k_scan_reduce(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tileSums, int numCells,
               const uint32_t* __restrict__ boundCells)
 {
     __shared__ uint32_t total;
     if (scan_tile_skipped(boundCells)) { if (threadIdx.x == 0) tileSums[blockIdx.x] = 0;  return; }
-    const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
     uint32_t s = 0;
-    if (base + 16 <= numCells) {
-        const uint4* p = reinterpret_cast<const uint4*>(cnt + base);
-        #pragma unroll
-        for (int k = 0; k < 4; k++) { uint4 q = p[k]; s += q.x + q.y + q.z + q.w; }
-    } else {
-        for (int k = 0; k < 16; k++) if (base + k < numCells) s += cnt[base + k];
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int base = blockIdx.x * SPH_SCAN_TILE + j * 1024 + threadIdx.x * 4;
+        if (base + 4 <= numCells) {
+            const uint4 q = *reinterpret_cast<const uint4*>(cnt + base);
+            s += q.x + q.y + q.z + q.w;
+        } else {
+            for (int k = 0; k < 4; k++) if (base + k < numCells) s += cnt[base + k];
+        }
     }
     block_excl_scan_256(s, &total);
     if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
@@ -317,53 +322,68 @@ __global__ void __launch_bounds__(256)
 k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const uint32_t* __restrict__ tileSums,
              uint32_t* __restrict__ maxCount, int numCells, int maxCells, const uint32_t* __restrict__ boundCells)
 {
-    __shared__ uint32_t total;
+    // exclusive offsets of (chunk j, warp w) in cell order: one warp scan over the 4 x 8 warp totals
+    __shared__ uint32_t warpExcl[32];
     if (scan_tile_skipped(boundCells)) return;
-    const int base = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * 16;
-    uint32_t c[16];
-    uint32_t s = 0, mx = 0;
-    const bool full = base + 16 <= numCells;
-    if (full) {
-        uint4* p = reinterpret_cast<uint4*>(cnt + base);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tile0 = blockIdx.x * SPH_SCAN_TILE;
+    uint32_t c[4][4], incl[4], mx = 0;
+    // all four loads first (the atomics of the big-cell list below would otherwise fence them into a chain)
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int base = tile0 + j * 1024 + threadIdx.x * 4;
+        if (base + 4 <= numCells) {
+            const uint4 q = *reinterpret_cast<const uint4*>(cnt + base);
+            c[j][0] = q.x;  c[j][1] = q.y;  c[j][2] = q.z;  c[j][3] = q.w;
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) c[j][k] = base + k < numCells ? cnt[base + k] : 0u;
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int base = tile0 + j * 1024 + threadIdx.x * 4;
+        if (base + 4 <= numCells) *reinterpret_cast<uint4*>(cnt + base) = make_uint4(0u, 0u, 0u, 0u);     // clean for the next step
+        else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (base + k < numCells) cnt[base + k] = 0;
+        }
         #pragma unroll
         for (int k = 0; k < 4; k++) {
-            uint4 q = p[k];
-            c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
-            p[k] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    } else {
-        #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            c[k] = 0;
-            if (base + k < numCells) { c[k] = cnt[base + k]; cnt[base + k] = 0; }
-        }
-    }
-    #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        s += c[k];
-        if (base + k < maxCells) {
-            mx = max(mx, c[k]);
-            // a cell too full for the per-entry counting of k_rank_gather goes on the list k_rank_big_cells works off
-            if (c[k] > (uint32_t)kBigCell) {
-                const uint32_t at = atomicAdd(maxCount + kBigCount, 1u);
-                if (at < (uint32_t)kBigCap) maxCount[kBigList + at] = (uint32_t)(base + k);
+            if (base + k < maxCells) {
+                mx = max(mx, c[j][k]);
+                // a cell too full for the per-entry counting of k_rank_gather goes on the list k_rank_big_cells works off
+                if (c[j][k] > (uint32_t)kBigCell) {
+                    const uint32_t at = atomicAdd(maxCount + kBigCount, 1u);
+                    if (at < (uint32_t)kBigCap) maxCount[kBigList + at] = (uint32_t)(base + k);
+                }
             }
         }
+        incl[j] = warp_incl_scan(c[j][0] + c[j][1] + c[j][2] + c[j][3]);
+        if (lane == 31) warpExcl[j * 8 + w] = incl[j];
     }
-    uint32_t ex = block_excl_scan_256(s, &total) + tileSums[blockIdx.x];
-    uint32_t o[16];
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t v = warpExcl[lane], iv = warp_incl_scan(v);
+        warpExcl[lane] = iv - v;
+    }
+    __syncthreads();
+    const uint32_t tileBase = tileSums[blockIdx.x];
     #pragma unroll
-    for (int k = 0; k < 16; k++) { o[k] = ex; ex += c[k]; }
-    if (full) {
-        uint4* p = reinterpret_cast<uint4*>(cellStart + base);
+    for (int j = 0; j < 4; j++) {
+        const int base = tile0 + j * 1024 + threadIdx.x * 4;
+        uint32_t ex = tileBase + warpExcl[j * 8 + w] + incl[j] - (c[j][0] + c[j][1] + c[j][2] + c[j][3]);
+        uint32_t o[4];
         #pragma unroll
-        for (int k = 0; k < 4; k++) p[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-    } else {
-        #pragma unroll
-        for (int k = 0; k < 16; k++) if (base + k < numCells) cellStart[base + k] = o[k];
+        for (int k = 0; k < 4; k++) { o[k] = ex;  ex += c[j][k]; }
+        if (base + 4 <= numCells) *reinterpret_cast<uint4*>(cellStart + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (base + k < numCells) cellStart[base + k] = o[k];
+        }
+        // cellStart[numCells] = n : the thread that owns the last cell writes it
+        if (base <= numCells - 1 && numCells - 1 < base + 4) cellStart[numCells] = o[numCells - 1 - base] + c[j][numCells - 1 - base];
     }
-    // cellStart[numCells] = n : the thread that owns the last cell writes it
-    if (base <= numCells - 1 && numCells - 1 < base + 16) cellStart[numCells] = ex;
 
     // largest cell population (decides whether the neighbour walk must truncate)
     #pragma unroll
