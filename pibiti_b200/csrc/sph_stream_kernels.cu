@@ -381,9 +381,8 @@ k_scan_apply(uint32_t* __restrict__ cnt, uint32_t* __restrict__ cellStart, const
             #pragma unroll
             for (int k = 0; k < 4; k++) if (base + k < numCells) cellStart[base + k] = o[k];
         }
-        // cellStart[numCells] = n : the thread that owns the last cell writes it (static indices: no local memory)
-        #pragma unroll
-        for (int k = 0; k < 4; k++) if (base + k == numCells - 1) cellStart[numCells] = o[k] + c[j][k];
+        // cellStart[numCells] = n : the thread that owns the last cell writes it
+        if (base <= numCells - 1 && numCells - 1 < base + 4) cellStart[numCells] = o[numCells - 1 - base] + c[j][numCells - 1 - base];
     }
 
     // largest cell population (decides whether the neighbour walk must truncate)

@@ -100,9 +100,14 @@ def test_staged_variant_uses_tma_bulk_copies(sass):
 
 def test_streaming_kernels_have_no_local_memory(resources):
     # (the integrate kernels index a float3 by axis in the cylinder / pump boundary branches: 32 bytes of stack there)
-    for needle in ("k_rank_gather", "k_bucket", "k_scan_apply", "k_scan_reduce", "k_slab_hash_hist"):
+    for needle in ("k_rank_gather", "k_bucket", "k_scan_reduce", "k_slab_hash_hist"):
         for res in _one(resources, needle):
             assert res["stack"] == 0 and res["local"] == 0, needle
+    # k_scan_apply indexes its per-thread cell values by a run-time position once (the thread that owns the LAST cell writes
+    # cellStart[numCells]): 80 bytes of stack.  The variant with static indices needs 64 registers instead of 48 and was
+    # measured slower (sort stage 0.137 vs 0.120 ms at 8M), so the small frame stays
+    for res in _one(resources, "k_scan_apply"):
+        assert res["stack"] <= 96 and res["reg"] <= 48
 
 
 def test_warp_collectives_carry_the_scan_and_the_slab_appends(sass):
