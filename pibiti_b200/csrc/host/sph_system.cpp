@@ -576,7 +576,7 @@ int cSPH::LoadState(const char* path)
     app.colliderPos = h.colliderPos;  app.dyePos = h.dyePos;  app.camPosLag = h.camPosLag;  app.camRotLag = h.camRotLag;
     if (h.curScene >= 0 && h.curScene < (int)scenes.size()) curScene = h.curScene;
     app.bChangedAny = false;                                // _InitMem uploaded scn.params
-    return sys || device < 0 ? SPH_OK : SPH_ERR_CUDA;
+    return sys || msys || device < 0 ? SPH_OK : SPH_ERR_CUDA;
 }
 
 // ---- scenes ------------------------------------------------------------------------------------

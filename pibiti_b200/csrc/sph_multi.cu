@@ -810,10 +810,14 @@ static int recut_one_process_per_slab(sph_multi* m)
         zc[k] = z = std::min(std::max(z, 0), gz - 1);
         hist[z]++;
     }
-    long long* dScratch = nullptr;
+    struct DeviceTemp {                         // freed on every way out, the early error returns included
+        void* p = nullptr;
+        ~DeviceTemp() { if (p) cudaFree(p); }
+    } scratchMem, newMem;
     const size_t scratchWords = (size_t)std::max(gz, W * W) + W;
-    MCU(m, cudaMalloc((void**)&dScratch, scratchWords * sizeof(long long)));
-    auto done = [&](int rc) { cudaFree(dScratch);  return rc; };
+    MCU(m, cudaMalloc(&scratchMem.p, scratchWords * sizeof(long long)));
+    long long* dScratch = static_cast<long long*>(scratchMem.p);
+    auto done = [&](int rc) { return rc; };
     MCU(m, cudaMemcpyAsync(dScratch, hist.data(), (size_t)gz * sizeof(long long), cudaMemcpyHostToDevice, r.xs));
     MNCCL(m, g_nccl.AllReduce(dScratch, dScratch, (size_t)gz, ncclInt64, ncclSum, r.comm, r.xs));
     MCU(m, cudaMemcpyAsync(hist.data(), dScratch, (size_t)gz * sizeof(long long), cudaMemcpyDeviceToHost, r.xs));
@@ -850,9 +854,9 @@ static int recut_one_process_per_slab(sph_multi* m)
 
     // particles travel device to device: everything leaves from the staging area, the new owned set is assembled in a
     // temporary buffer (kept block first, then one block per sender)
-    float* dNew = nullptr;
-    MCU(m, cudaMalloc((void**)&dNew, (size_t)std::max<long long>(total, 1) * kRecFloats * sizeof(float)));
-    auto done2 = [&](int rc) { cudaFree(dNew);  return done(rc); };
+    MCU(m, cudaMalloc(&newMem.p, (size_t)std::max<long long>(total, 1) * kRecFloats * sizeof(float)));
+    float* dNew = static_cast<float*>(newMem.p);
+    auto done2 = [&](int rc) { return done(rc); };
     if (count > 0) MCU(m, cudaMemcpyAsync(stage, binned.data(), (size_t)count * kRecFloats * sizeof(float), cudaMemcpyHostToDevice, r.xs));
     if (kept > 0) MCU(m, cudaMemcpyAsync(dNew, stage + (size_t)off[me] * kRecFloats, (size_t)kept * kRecFloats * sizeof(float), cudaMemcpyDeviceToDevice, r.xs));
     MNCCL(m, g_nccl.GroupStart());

@@ -175,6 +175,30 @@ def test_multi_driver_nccl_two_processes(tmp_path):
     assert np.array_equal(got["pos"], ref[0]) and np.array_equal(got["vel"], ref[1]) and np.array_equal(got["dens"], ref[2])
 
 
+def test_csph_device_list_checkpoint_round_trip(tmp_path):
+    """SaveState / LoadState through the host mirrors of a multi-GPU cSPH: a run resumed from the file (into a fresh
+    one-device object) continues exactly like the uninterrupted multi-GPU run."""
+    a = host.CSph(device=0, devices=[0, 0])
+    a.select_scene("mini waves")
+    for _ in range(4):
+        a.UpdateEmitter()
+        a.Update()
+    a.SaveState(tmp_path / "multi.ckp")
+    for _ in range(3):
+        a.UpdateEmitter()
+        a.Update()
+    want = a.getArray(False).copy(), a.getArray(True).copy()
+    a.close()
+    for devices in (None, [0, 0, 0]):
+        b = host.CSph(device=0, devices=devices)
+        b.LoadState(tmp_path / "multi.ckp")
+        for _ in range(3):
+            b.UpdateEmitter()
+            b.Update()
+        assert np.array_equal(b.getArray(False), want[0]) and np.array_equal(b.getArray(True), want[1]), devices
+        b.close()
+
+
 def test_csph_with_a_device_list_equals_one_device():
     """cSPH(device list): Reset through the mirrors, a full-range setArray, steps, a PARTIAL setArray mid-run (what an
     emitter does) and getArray -- identical to the one-device cSPH."""
