@@ -421,10 +421,12 @@ extern "C" int sph_multi_create(const struct SimParams* params, int ndev, const 
         for (int k = 0; k + 1 < ndev; k++) {
             const int a = devices[k], b = devices[k + 1];
             if (a == b) continue;
-            int ok = 0;
-            if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok) { cudaSetDevice(a);  cudaDeviceEnablePeerAccess(b, 0); }
-            if (cudaDeviceCanAccessPeer(&ok, b, a) == cudaSuccess && ok) { cudaSetDevice(b);  cudaDeviceEnablePeerAccess(a, 0); }
+            int ab = 0, ba = 0;
+            if (cudaDeviceCanAccessPeer(&ab, a, b) == cudaSuccess && ab) { cudaSetDevice(a);  cudaDeviceEnablePeerAccess(b, 0); }
+            if (cudaDeviceCanAccessPeer(&ba, b, a) == cudaSuccess && ba) { cudaSetDevice(b);  cudaDeviceEnablePeerAccess(a, 0); }
             cudaGetLastError();                 // "already enabled" is fine
+            // copies work without peer access (staged through the host); kernel-side peer stores do not
+            if (!(ab && ba)) m->peerStores = false;
         }
     }
     if (rc == SPH_OK && ndev > 1 && !m->copyExchange) {
